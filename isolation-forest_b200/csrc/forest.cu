@@ -1,0 +1,569 @@
+// Forest handles: validation of the persisted node tables, relayout into the kernel layout, upload.
+//
+// Replaces the broadcast object graph of the reference (IF/Nodes.scala:25-66,
+// IF/extended/ExtendedNodes.scala:28-63; broadcast at IF/IsolationForestModel.scala:129).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <queue>
+
+#include "ifb_internal.h"
+
+namespace ifb {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+static std::atomic_llong g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Utils.avgPathLength, IF/core/Utils.scala:85-92: f32 arithmetic around an f64 log rounded to f32.
+float avg_path_length_host(int64_t n) {
+    if (n <= 1) return 0.0f;
+    const float euler = 0.5772156649f;
+    volatile float nf = (float)n;
+    volatile float lg = (float)std::log((double)(nf - 1.0f));
+    volatile float a = 2.0f * (lg + euler);
+    volatile float b = (2.0f * (nf - 1.0f)) / nf;
+    return a - b;
+}
+
+int device_smem_optin(int device) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    return v;
+}
+int device_sm_count(int device) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    return v;
+}
+
+// Smallest f32 >= t.  For an f32 x:  (double)x < t  <=>  x < ceil32(t)   (proof in DESIGN.md).
+static float ceil_to_f32(double t) {
+    float f = (float)t;  // round to nearest
+    if ((double)f < t) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+// Shape validation shared by both variants.  Mirrors what the reference's loader enforces
+// (IF/IsolationForestModelReadWrite.scala:179-205: ids 0..n-1 in pre-order, children resolvable).
+static int validate_shape(int32_t T, const int32_t *node_off, const int32_t *left, const int32_t *right,
+                          const int64_t *num_instances, bool allow_empty_leaf) {
+    IFB_REQUIRE(T >= 0, "num_trees must be >= 0, got %d", T);
+    IFB_REQUIRE(node_off && (T == 0 || (left && right && num_instances)), "null node table");
+    IFB_REQUIRE(node_off[0] == 0, "node_off[0] must be 0");
+    for (int t = 0; t < T; t++) {
+        int32_t n = node_off[t + 1] - node_off[t];
+        IFB_REQUIRE(n >= 1, "tree %d has no nodes", t);
+        const int32_t base = node_off[t];
+        std::vector<uint8_t> seen(n, 0);
+        seen[0] = 1;
+        for (int32_t i = 0; i < n; i++) {
+            int32_t l = left[base + i], r = right[base + i];
+            if (l == -1 || r == -1) {
+                IFB_REQUIRE(l == -1 && r == -1, "tree %d node %d: half-leaf (left=%d right=%d)", t, i, l, r);
+                int64_t c = num_instances[base + i];
+                IFB_REQUIRE(allow_empty_leaf ? c >= 0 : c > 0,
+                            "tree %d node %d: leaf numInstances %lld is invalid", t, i, (long long)c);
+            } else {
+                // pre-order: left child is the next row, right child comes later
+                IFB_REQUIRE(l == i + 1 && r > l && r < n, "tree %d node %d: children (%d,%d) not in pre-order", t, i,
+                            l, r);
+                IFB_REQUIRE(!seen[l] && !seen[r], "tree %d node %d: child visited twice", t, i);
+                seen[l] = seen[r] = 1;
+            }
+        }
+        for (int32_t i = 0; i < n; i++) IFB_REQUIRE(seen[i], "tree %d node %d is unreachable", t, i);
+    }
+    return IFB_OK;
+}
+
+// BFS order of one tree: order[k] = pre-order id of the k-th BFS node, children of a node adjacent.
+static void bfs_order(const int32_t *left, const int32_t *right, int32_t n, std::vector<int32_t> &order,
+                      std::vector<int32_t> &depth_of_bfs) {
+    order.clear();
+    depth_of_bfs.clear();
+    order.reserve(n);
+    order.push_back(0);
+    depth_of_bfs.push_back(0);
+    for (size_t h = 0; h < order.size(); h++) {
+        int32_t id = order[h];
+        if (left[id] != -1) {
+            order.push_back(left[id]);
+            depth_of_bfs.push_back(depth_of_bfs[h] + 1);
+            order.push_back(right[id]);
+            depth_of_bfs.push_back(depth_of_bfs[h] + 1);
+        }
+    }
+}
+
+int build_standard_tables(ifb_forest *f) {
+    const int T = f->num_trees;
+    const int64_t total = f->node_off[T];
+    f->h_val.assign(total, 0.f);
+    f->h_meta_feat.assign(total, 0xFFFFFFFFu);
+    f->h_child.assign(total, -1);
+    f->h_depth.assign(total, 0);
+    f->bfs_off.assign(f->node_off.begin(), f->node_off.end());
+    f->max_depth = 0;
+    f->max_feature_index = -1;
+    std::vector<int32_t> order, dep, pos;
+    for (int t = 0; t < T; t++) {
+        const int32_t base = f->node_off[t], n = f->node_off[t + 1] - base;
+        bfs_order(&f->left[base], &f->right[base], n, order, dep);
+        pos.assign(n, 0);
+        for (int32_t k = 0; k < n; k++) pos[order[k]] = k;
+        for (int32_t k = 0; k < n; k++) {
+            const int32_t id = order[k];
+            const int64_t g = base + k;
+            IFB_REQUIRE(dep[k] <= 250, "tree %d deeper than 250 levels", t);
+            f->h_depth[g] = (uint8_t)dep[k];
+            if (f->left[base + id] == -1) {
+                // leaf value = currentPathLength (exact small integer in f32) + avgPathLength(n):
+                // one f32 add, exactly as IF/IsolationTree.scala:218.
+                volatile float v = (float)dep[k] + avg_path_length_host(f->num_instances[base + id]);
+                f->h_val[g] = v;
+                f->max_depth = std::max(f->max_depth, dep[k]);
+            } else {
+                f->h_val[g] = ceil_to_f32(f->threshold[base + id]);
+                f->h_meta_feat[g] = (uint32_t)f->feature[base + id];
+                f->h_child[g] = pos[f->left[base + id]];
+                f->max_feature_index = std::max(f->max_feature_index, f->feature[base + id]);
+            }
+        }
+    }
+    return IFB_OK;
+}
+
+int build_extended_tables(ifb_forest *f) {
+    const int T = f->num_trees;
+    const int64_t total = f->node_off[T];
+    const int k = f->max_nnz;
+    std::vector<double> off(total, 0.0);
+    std::vector<float> leaf(total, 0.f);
+    std::vector<int32_t> child(total, -1), hp(total, -1), len(total, 0);
+    std::vector<int64_t> tree_node(f->node_off.begin(), f->node_off.end());
+    int64_t internal = 0;
+    for (int64_t g = 0; g < total; g++) internal += (f->left[g] != -1);
+    std::vector<float> w((size_t)internal * k, 0.f);
+    std::vector<int32_t> idx((size_t)internal * k, 0);
+    bool identity = true;
+    f->max_depth = 0;
+    std::vector<int32_t> order, dep, pos;
+    int64_t slot = 0;
+    for (int t = 0; t < T; t++) {
+        const int32_t base = f->node_off[t], n = f->node_off[t + 1] - base;
+        bfs_order(&f->left[base], &f->right[base], n, order, dep);
+        pos.assign(n, 0);
+        for (int32_t q = 0; q < n; q++) pos[order[q]] = q;
+        for (int32_t q = 0; q < n; q++) {
+            const int32_t id = order[q];
+            const int64_t g = base + q, src = base + id;
+            if (f->left[src] == -1) {
+                volatile float v = (float)dep[q] + avg_path_length_host(f->num_instances[src]);
+                leaf[g] = v;
+                f->max_depth = std::max(f->max_depth, dep[q]);
+            } else {
+                off[g] = f->offset[src];
+                child[g] = pos[f->left[src]];
+                hp[g] = (int32_t)slot;
+                const int64_t b = f->hp_off[src], e = f->hp_off[src + 1];
+                len[g] = (int32_t)(e - b);
+                // Rows narrower than k are padded (index of the last term, weight 0); kernels stop at len.
+                for (int64_t i = 0; i < k; i++) {
+                    const int64_t s = b + std::min<int64_t>(i, e - b - 1);
+                    idx[slot * k + i] = f->hp_idx[s];
+                    w[slot * k + i] = (i < e - b) ? f->hp_w[s] : 0.0f;
+                    if (idx[slot * k + i] != i) identity = false;
+                }
+                if (e - b != k) identity = false;
+                slot++;
+            }
+        }
+    }
+    f->ext_internal_slots = internal;
+    f->ext_dense_identity = identity && internal > 0;
+    DeviceGuard dg(f->device);
+    auto up = [&](void **dptr, const void *src, size_t bytes) -> int {
+        if (bytes == 0) bytes = 16;
+        IFB_CUDA(cudaMalloc(dptr, bytes));
+        if (src) IFB_CUDA(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+        f->device_bytes += (int64_t)bytes;
+        return IFB_OK;
+    };
+    int rc;
+    if ((rc = up((void **)&f->d_ext_w, w.data(), w.size() * 4))) return rc;
+    if (!f->ext_dense_identity)
+        if ((rc = up((void **)&f->d_ext_idx, idx.data(), idx.size() * 4))) return rc;
+    if ((rc = up((void **)&f->d_ext_off, off.data(), off.size() * 8))) return rc;
+    if ((rc = up((void **)&f->d_ext_leaf, leaf.data(), leaf.size() * 4))) return rc;
+    if ((rc = up((void **)&f->d_ext_child, child.data(), child.size() * 4))) return rc;
+    if ((rc = up((void **)&f->d_ext_hp, hp.data(), hp.size() * 4))) return rc;
+    if ((rc = up((void **)&f->d_ext_len, len.data(), len.size() * 4))) return rc;
+    if ((rc = up((void **)&f->d_ext_tree_node, tree_node.data(), tree_node.size() * 8))) return rc;
+    return IFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Standard-forest shared-memory plan for a given feature count d.
+//   smem = [ val words | meta words ] of one chunk  +  stages * (d+1) * R floats of row tiles + barriers
+// ------------------------------------------------------------------------------------------------
+int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
+    std::lock_guard<std::mutex> lk(f->plan_mu);
+    for (auto *p : f->std_plans)
+        if (p->d == d) {
+            *out = p;
+            return IFB_OK;
+        }
+    IFB_REQUIRE(d >= 1 && d <= 4094, "standard scoring supports 1 <= d <= 4094 features, got %d", d);
+    IFB_REQUIRE(f->max_feature_index < d, "forest reads feature index %d but the matrix has only %d columns",
+                f->max_feature_index, d);
+    const int smem_max = device_smem_optin(f->device);
+    IFB_REQUIRE(smem_max >= 200 * 1024, "device %d offers only %d bytes of shared memory per block", f->device,
+                smem_max);
+    const int T = f->num_trees;
+    int64_t largest_tree = 0;
+    for (int t = 0; t < T; t++) largest_tree = std::max<int64_t>(largest_tree, f->bfs_off[t + 1] - f->bfs_off[t]);
+    const int64_t total_nodes = f->bfs_off[T];
+
+    // pick the widest row tile that leaves room for the whole forest if possible, else for >= 48 KB of it
+    auto *p = new ifb_forest::StdPlan();
+    p->d = d;
+    const int64_t overhead = 1024;  // barriers, tree-root table slack, alignment
+    // Row-tile width R (= threads per CTA).  Prefer the widest tile that still leaves room for the whole
+    // forest (single pass over the matrix); otherwise the widest tile <= 256 rows that leaves >= 64 KB for
+    // one chunk of trees (several passes, sums carried in path_sum between them).
+    const int64_t need_whole = (total_nodes + 1) * 8 + (int64_t)T * 4;
+    const int64_t need_one = (largest_tree + 1) * 8 + 64;
+    auto room_for = [&](int cand) { return (int64_t)smem_max - overhead - 2LL * (d + 1) * cand * 4; };
+    int R = 0;
+    for (int cand : {512, 256, 128, 64, 32})
+        if (room_for(cand) >= std::max(need_whole, need_one)) {
+            R = cand;
+            break;
+        }
+    if (R == 0)
+        for (int cand : {256, 128, 64, 32})
+            if (room_for(cand) >= std::max<int64_t>(64 * 1024, need_one)) {
+                R = cand;
+                break;
+            }
+    if (R == 0 && room_for(32) >= need_one) R = 32;
+    if (R == 0) {
+        delete p;
+        set_error("no shared-memory plan for d=%d (largest tree %lld nodes)", d, (long long)largest_tree);
+        return IFB_EINVAL;
+    }
+    p->rows_per_tile = R;
+    const int64_t room = smem_max - overhead - 2LL * (d + 1) * R * 4;
+    // greedy chunking; each chunk: 1 pad word + nodes, plus 4 bytes per tree for the root table
+    std::vector<float> val;
+    std::vector<uint32_t> meta, roots(T, 0);
+    int t = 0;
+    while (t < T) {
+        StdChunk c;
+        c.tree_begin = t;
+        c.node_begin = (int32_t)val.size();
+        int64_t words = 1;  // pad slot 0 so that "self - 1" of a root leaf is valid
+        int64_t trees = 0;
+        while (t < T) {
+            int64_t n = f->bfs_off[t + 1] - f->bfs_off[t];
+            if ((words + n) * 8 + (trees + 1) * 4 > room && trees > 0) break;
+            words += n;
+            trees++;
+            t++;
+        }
+        c.tree_end = t;
+        c.node_count = (int32_t)words;
+        IFB_REQUIRE(words * 4 < (1 << 20), "chunk too large for 20-bit child offsets");
+        val.push_back(0.f);
+        meta.push_back(0u);
+        int64_t w = 1;
+        for (int tt = c.tree_begin; tt < c.tree_end; tt++) {
+            const int32_t base = f->bfs_off[tt], n = f->bfs_off[tt + 1] - base;
+            roots[tt] = (uint32_t)(w * 4);  // byte offset of the root inside the chunk's val array
+            for (int32_t q = 0; q < n; q++) {
+                const int64_t g = base + q;
+                const int64_t self = w + q;
+                val.push_back(f->h_val[g]);
+                if (f->h_child[g] < 0) {
+                    meta.push_back(((uint32_t)d << 20) | (uint32_t)((self - 1) * 4));
+                } else {
+                    meta.push_back((f->h_meta_feat[g] << 20) | (uint32_t)((w + f->h_child[g]) * 4));
+                }
+            }
+            w += n;
+        }
+        p->chunks.push_back(c);
+    }
+    p->total_words = (int64_t)val.size();
+    DeviceGuard dg(f->device);
+    IFB_CUDA(cudaMalloc((void **)&p->d_val, std::max<size_t>(16, val.size() * 4)));
+    IFB_CUDA(cudaMalloc((void **)&p->d_meta, std::max<size_t>(16, meta.size() * 4)));
+    IFB_CUDA(cudaMalloc((void **)&p->d_tree_root, std::max<size_t>(16, roots.size() * 4)));
+    IFB_CUDA(cudaMemcpy(p->d_val, val.data(), val.size() * 4, cudaMemcpyHostToDevice));
+    IFB_CUDA(cudaMemcpy(p->d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+    IFB_CUDA(cudaMemcpy(p->d_tree_root, roots.data(), roots.size() * 4, cudaMemcpyHostToDevice));
+    f->device_bytes += (int64_t)(val.size() * 8 + roots.size() * 4);
+    f->std_plans.push_back(p);
+    *out = p;
+    return IFB_OK;
+}
+
+}  // namespace ifb
+
+ifb_forest::~ifb_forest() {
+    ifb::DeviceGuard dg(device);
+    for (auto *p : std_plans) {
+        cudaFree(p->d_val);
+        cudaFree(p->d_meta);
+        cudaFree(p->d_tree_root);
+        delete p;
+    }
+    cudaFree(d_ext_w);
+    cudaFree(d_ext_idx);
+    cudaFree(d_ext_off);
+    cudaFree(d_ext_leaf);
+    cudaFree(d_ext_child);
+    cudaFree(d_ext_hp);
+    cudaFree(d_ext_len);
+    cudaFree(d_ext_tree_node);
+}
+
+using namespace ifb;
+
+extern "C" {
+
+int ifb_abi_version(void) { return IFB_ABI_VERSION; }
+const char *ifb_last_error(void) { return g_last_error.c_str(); }
+float ifb_avg_path_length(int64_t n) { return avg_path_length_host(n); }
+int64_t ifb_kernel_launch_count(int32_t reset) {
+    return reset ? (int64_t)g_launches.exchange(0) : (int64_t)g_launches.load();
+}
+
+int ifb_device_count(int32_t *count) {
+    IFB_REQUIRE(count, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        set_error("no CUDA device: %s", cudaGetErrorString(e));
+        return IFB_ENOGPU;
+    }
+    *count = n;
+    return IFB_OK;
+}
+
+int ifb_host_alloc(size_t bytes, void **ptr) {
+    IFB_REQUIRE(ptr, "ptr is null");
+    IFB_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return IFB_OK;
+}
+int ifb_host_free(void *ptr) {
+    if (ptr) IFB_CUDA(cudaFreeHost(ptr));
+    return IFB_OK;
+}
+int ifb_device_alloc(int32_t device, size_t bytes, void **ptr) {
+    IFB_REQUIRE(ptr, "ptr is null");
+    DeviceGuard dg(device);
+    IFB_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+    return IFB_OK;
+}
+int ifb_device_free(int32_t device, void *ptr) {
+    DeviceGuard dg(device);
+    if (ptr) IFB_CUDA(cudaFree(ptr));
+    return IFB_OK;
+}
+
+static int check_device(int32_t device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); this engine has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return IFB_ENOGPU;
+    }
+    IFB_REQUIRE(device >= 0 && device < n, "device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    IFB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return IFB_ENOGPU;
+    }
+    return IFB_OK;
+}
+
+int ifb_forest_create_standard(int32_t device, int32_t num_trees, const int32_t *node_off, const int32_t *left,
+                               const int32_t *right, const int32_t *feature, const double *threshold,
+                               const int64_t *num_instances, int32_t num_samples, int32_t total_num_features,
+                               ifb_forest **out) {
+    IFB_REQUIRE(out, "out is null");
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    // IsolationForestModel constructor requires (IF/IsolationForestModel.scala:61-78)
+    IFB_REQUIRE(num_samples > 0, "parameter numSamples must be >0, but given invalid value %d", num_samples);
+    IFB_REQUIRE(total_num_features == -1 || total_num_features > 0,
+                "parameter totalNumFeatures must be >0 or UnknownTotalNumFeatures, but given invalid value %d",
+                total_num_features);
+    rc = validate_shape(num_trees, node_off, left, right, num_instances, /*allow_empty_leaf=*/false);
+    if (rc) return rc;
+    const int64_t total = node_off[num_trees];
+    IFB_REQUIRE(total == 0 || (feature && threshold), "null split table");
+    for (int64_t g = 0; g < total; g++) {
+        if (left[g] != -1) {
+            // InternalNode requires splitAttribute >= 0 (IF/Nodes.scala:55-59)
+            IFB_REQUIRE(feature[g] >= 0, "node %lld: splitAttribute %d must be >= 0", (long long)g, feature[g]);
+            IFB_REQUIRE(total_num_features == -1 || feature[g] < total_num_features,
+                        "node %lld: splitAttribute %d outside the %d training features", (long long)g, feature[g],
+                        total_num_features);
+            IFB_REQUIRE(!std::isnan(threshold[g]), "node %lld: splitValue is NaN", (long long)g);
+        }
+    }
+    auto *f = new ifb_forest();
+    f->device = device;
+    f->extended = false;
+    f->num_trees = num_trees;
+    f->num_samples = num_samples;
+    f->total_num_features = total_num_features;
+    f->avg_path_norm = avg_path_length_host(num_samples);
+    f->node_off.assign(node_off, node_off + num_trees + 1);
+    f->left.assign(left, left + total);
+    f->right.assign(right, right + total);
+    f->feature.assign(feature, feature + total);
+    f->threshold.assign(threshold, threshold + total);
+    f->num_instances.assign(num_instances, num_instances + total);
+    rc = build_standard_tables(f);
+    if (rc) {
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return IFB_OK;
+}
+
+int ifb_forest_create_extended(int32_t device, int32_t num_trees, const int32_t *node_off, const int32_t *left,
+                               const int32_t *right, const int64_t *num_instances, const double *offset,
+                               const int64_t *hp_off, const int32_t *hp_idx, const float *hp_w,
+                               int32_t num_samples, int32_t total_num_features, ifb_forest **out) {
+    IFB_REQUIRE(out, "out is null");
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    IFB_REQUIRE(num_samples > 0, "parameter numSamples must be >0, but given invalid value %d", num_samples);
+    IFB_REQUIRE(total_num_features == -1 || total_num_features > 0,
+                "parameter totalNumFeatures must be >0 or UnknownTotalNumFeatures, but given invalid value %d",
+                total_num_features);
+    // ExtendedExternalNode allows numInstances == 0 (IF/extended/ExtendedNodes.scala:28-38)
+    rc = validate_shape(num_trees, node_off, left, right, num_instances, /*allow_empty_leaf=*/true);
+    if (rc) return rc;
+    const int64_t total = node_off[num_trees];
+    IFB_REQUIRE(total == 0 || (offset && hp_off), "null hyperplane table");
+    IFB_REQUIRE(total == 0 || hp_off[0] == 0, "hp_off[0] must be 0");
+    int32_t max_nnz = 1, max_idx = -1;
+    for (int64_t g = 0; g < total; g++) {
+        const int64_t b = hp_off[g], e = hp_off[g + 1];
+        IFB_REQUIRE(e >= b, "hp_off not monotone at node %lld", (long long)g);
+        if (left[g] == -1) {
+            IFB_REQUIRE(e == b, "leaf node %lld carries a hyperplane", (long long)g);
+            continue;
+        }
+        // SplitHyperplane invariants (IF/extended/ExtendedUtils.scala:27-34)
+        IFB_REQUIRE(e > b, "indices must be non-empty.");
+        IFB_REQUIRE(e - b <= (1 << 20), "hyperplane too wide");
+        IFB_REQUIRE(hp_idx && hp_w, "null hyperplane arrays");
+        for (int64_t i = b; i < e; i++) {
+            IFB_REQUIRE(hp_idx[i] >= 0, "indices must be non-negative.");
+            IFB_REQUIRE(i == b || hp_idx[i] != hp_idx[i - 1], "indices must be distinct.");
+            IFB_REQUIRE(i == b || hp_idx[i] > hp_idx[i - 1], "indices must be sorted in ascending order.");
+            IFB_REQUIRE(total_num_features == -1 || hp_idx[i] < total_num_features,
+                        "hyperplane index %d outside the %d training features", hp_idx[i], total_num_features);
+            max_idx = std::max(max_idx, hp_idx[i]);
+        }
+        IFB_REQUIRE(!std::isnan(offset[g]), "node %lld: offset is NaN", (long long)g);
+        max_nnz = std::max<int32_t>(max_nnz, (int32_t)(e - b));
+    }
+    auto *f = new ifb_forest();
+    f->device = device;
+    f->extended = true;
+    f->num_trees = num_trees;
+    f->num_samples = num_samples;
+    f->total_num_features = total_num_features;
+    f->avg_path_norm = avg_path_length_host(num_samples);
+    f->max_nnz = max_nnz;
+    f->max_feature_index = max_idx;
+    f->node_off.assign(node_off, node_off + num_trees + 1);
+    f->left.assign(left, left + total);
+    f->right.assign(right, right + total);
+    f->offset.assign(offset, offset + total);
+    f->num_instances.assign(num_instances, num_instances + total);
+    f->hp_off.assign(hp_off, hp_off + total + 1);
+    const int64_t nh = total ? hp_off[total] : 0;
+    f->hp_idx.assign(hp_idx, hp_idx + nh);
+    f->hp_w.assign(hp_w, hp_w + nh);
+    rc = build_extended_tables(f);
+    if (rc) {
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return IFB_OK;
+}
+
+int ifb_forest_destroy(ifb_forest *forest) {
+    delete forest;
+    return IFB_OK;
+}
+
+int ifb_forest_get_info(const ifb_forest *f, ifb_forest_info *info) {
+    IFB_REQUIRE(f && info, "null argument");
+    info->extended = f->extended;
+    info->device = f->device;
+    info->num_trees = f->num_trees;
+    info->num_samples = f->num_samples;
+    info->total_num_features = f->total_num_features;
+    info->max_feature_index = f->max_feature_index;
+    info->max_depth = f->max_depth;
+    info->max_nnz = f->max_nnz;
+    info->num_nodes = f->node_off.empty() ? 0 : f->node_off.back();
+    info->num_hp_entries = (int64_t)f->hp_idx.size();
+    info->device_bytes = f->device_bytes;
+    return IFB_OK;
+}
+
+int ifb_forest_export(const ifb_forest *f, int32_t *node_off, int32_t *left, int32_t *right, int32_t *feature,
+                      double *threshold, int64_t *num_instances, double *offset, int64_t *hp_off,
+                      int32_t *hp_idx, float *hp_w) {
+    IFB_REQUIRE(f, "forest is null");
+    auto cp = [](auto *dst, const auto &v) {
+        if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+    };
+    cp(node_off, f->node_off);
+    cp(left, f->left);
+    cp(right, f->right);
+    cp(num_instances, f->num_instances);
+    if (f->extended) {
+        cp(offset, f->offset);
+        cp(hp_off, f->hp_off);
+        cp(hp_idx, f->hp_idx);
+        cp(hp_w, f->hp_w);
+    } else {
+        cp(feature, f->feature);
+        cp(threshold, f->threshold);
+    }
+    return IFB_OK;
+}
+
+}  // extern "C"

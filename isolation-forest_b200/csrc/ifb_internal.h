@@ -1,0 +1,165 @@
+// Internal declarations shared by the translation units of libifb200.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "ifb200.h"
+
+namespace ifb {
+
+void set_error(const char *fmt, ...);
+
+#define IFB_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::ifb::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,      \
+                             __LINE__, cudaGetErrorString(_e));                                 \
+            return _e == cudaErrorMemoryAllocation ? IFB_ENOMEM : IFB_ECUDA;                    \
+        }                                                                                       \
+    } while (0)
+
+#define IFB_REQUIRE(cond, ...)             \
+    do {                                   \
+        if (!(cond)) {                     \
+            ::ifb::set_error(__VA_ARGS__); \
+            return IFB_EINVAL;             \
+        }                                  \
+    } while (0)
+
+void count_launch(int n = 1);
+
+// RAII device guard
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Device-side node tables ("kernel layout").
+//
+// Standard forest.  Every tree is renumbered in level order (BFS) with the two children of a node
+// adjacent (right = left + 1).  One node = two 32-bit words kept in two parallel arrays so that a warp
+// whose lanes sit on different nodes of one level touches distinct banks for the top levels:
+//     val [g] : internal: smallest f32 >= splitValue  (x < splitValue  <=>  x < val, x being f32)
+//               leaf    : (float)depth + avgPathLength(numInstances)   (the value pathLength returns)
+//     meta[g] : (feature << 20) | child_off   where child_off (20 bits) = BYTE offset of the LEFT child in
+//               the chunk-local val[] array; leaves store feature = d (the pseudo column of NaNs every
+//               row tile carries) and child_off = self - 4, so "next = child_off + 4*!(x < val)" maps a
+//               leaf onto itself: walks run a fixed number of steps with no per-level branch.
+// Trees are grouped into chunks whose tables fit in shared memory next to the row tiles.
+// ------------------------------------------------------------------------------------------------
+struct StdChunk {
+    int32_t tree_begin = 0, tree_end = 0;
+    int32_t node_begin = 0, node_count = 0;  // slice of the device arrays (node_count includes 1 pad slot)
+};
+
+struct ExtTreeDesc {          // one per tree, extended forests
+    int64_t node_begin;       // first node (BFS order) in the device arrays
+    int32_t node_count;
+    int32_t depth;            // deepest leaf
+};
+
+}  // namespace ifb
+
+struct ifb_forest {
+    int32_t device = 0;
+    bool extended = false;
+    int32_t num_trees = 0;
+    int32_t num_samples = 0;
+    int32_t total_num_features = -1;
+    int32_t max_feature_index = -1;
+    int32_t max_depth = 0;
+    int32_t max_nnz = 1;
+    float avg_path_norm = 0.f;  // c(numSamples)
+
+    // persisted layout (host copy; what ifb_forest_export returns)
+    std::vector<int32_t> node_off, left, right, feature;
+    std::vector<double> threshold, offset;
+    std::vector<int64_t> num_instances, hp_off;
+    std::vector<int32_t> hp_idx;
+    std::vector<float> hp_w;
+
+    // ---- standard kernel layout ----
+    // host mirrors are kept so that chunking can be re-planned for a different feature count
+    std::vector<float> h_val;
+    std::vector<uint32_t> h_meta_feat;   // feature per node (d placeholder = 0xFFFFFFFF for leaves)
+    std::vector<int32_t> h_child;        // tree-local BFS index of left child, or -1 for leaf
+    std::vector<uint8_t> h_depth;        // depth of the node
+    std::vector<int32_t> bfs_off;        // [T+1] first BFS node of each tree (== node_off)
+
+    // plans are keyed by the feature count d of the scored matrix (pseudo column index + smem budget)
+    struct StdPlan {
+        int32_t d = -1;
+        int32_t rows_per_tile = 0;
+        std::vector<ifb::StdChunk> chunks;
+        float *d_val = nullptr;
+        uint32_t *d_meta = nullptr;
+        uint32_t *d_tree_root = nullptr;  // [T] chunk-local word index of each tree's root
+        int64_t total_words = 0;
+    };
+    std::mutex plan_mu;
+    std::vector<StdPlan *> std_plans;
+
+    // ---- extended kernel layout ----
+    // BFS order per tree; hyperplanes stored densely per internal node with a fixed width k = max_nnz.
+    float *d_ext_w = nullptr;          // [internal_slots * k]
+    int32_t *d_ext_idx = nullptr;      // [internal_slots * k] (nullptr when every hyperplane is the identity 0..k-1)
+    double *d_ext_off = nullptr;       // [nodes] split offset (internal) / unused (leaf)
+    float *d_ext_leaf = nullptr;       // [nodes] (float)depth + c(n) at leaves
+    int32_t *d_ext_child = nullptr;    // [nodes] left child (tree-local BFS) or -1 at leaves
+    int32_t *d_ext_hp = nullptr;       // [nodes] hyperplane slot (index into w/idx rows) or -1 at leaves
+    int32_t *d_ext_len = nullptr;      // [nodes] number of hyperplane terms (0 at leaves)
+    int64_t *d_ext_tree_node = nullptr;  // [T+1]
+    bool ext_dense_identity = false;
+    int64_t ext_internal_slots = 0;
+
+    int64_t device_bytes = 0;
+
+    ~ifb_forest();
+};
+
+namespace ifb {
+
+// forest.cu
+int build_standard_tables(ifb_forest *f);
+int build_extended_tables(ifb_forest *f);
+int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out);
+
+// score_std.cu
+int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const float *X, int64_t n_rows,
+                          int32_t d, int64_t ld, int32_t layout, double *scores, int32_t *depth_sum,
+                          float *path_sum, bool accumulate_only, cudaStream_t stream);
+// score_ext.cu
+int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld,
+                          int32_t layout, double *scores, int32_t *depth_sum, float *path_sum,
+                          bool accumulate_only, cudaStream_t stream);
+// epilogue.cu
+int launch_finalize(const float *path_sum, int64_t n_rows, int32_t total_trees, float avg_path, double *scores,
+                    cudaStream_t stream);
+int launch_predict(const double *scores, int64_t n_rows, double threshold, double *labels, cudaStream_t stream);
+int launch_transpose(const float *in, int64_t n, int32_t d, int64_t ld_in, float *out, int64_t ld_out,
+                     cudaStream_t stream);
+int launch_select(const double *scores, int64_t n, int64_t rank0, double *value, unsigned long long *count_ge,
+                  cudaStream_t stream);
+
+float avg_path_length_host(int64_t n);
+int device_smem_optin(int device);
+int device_sm_count(int device);
+
+}  // namespace ifb

@@ -1,0 +1,388 @@
+// Standard isolation-forest scoring for sm_100a.
+//
+// Replaces the per-row UDF of IsolationForestModel.transform (IF/IsolationForestModel.scala:131-139) and
+// the tail-recursive walk IsolationTree.pathLength (IF/IsolationTree.scala:196-230).
+//
+// Shape of the kernel (DESIGN.md "score_standard"):
+//   * persistent grid, one CTA per SM, R threads; thread r owns row r of the current row tile;
+//   * the node tables of one forest chunk (val[] / meta[] words, see ifb_internal.h) are copied into
+//     shared memory once per CTA;
+//   * row tiles stream through a 2-stage shared-memory ring filled by TMA (cp.async.bulk.tensor.2d on a
+//     tensor map over the column-major matrix; box = RB rows x <=256 features, landing as [feature][RB] so
+//     that lane r reads bank r%32 whatever feature its node asks for) and signalled through mbarriers;
+//   * a walk is a fixed number of steps (the forest's max depth); leaves map onto themselves through the
+//     NaN pseudo feature, so there is no per-level branch; C trees are walked at once per thread for ILP;
+//   * per-row path lengths are added in tree order in f32 (Array[Float].sum), then
+//     score = exp2(-(s/T)/c(numSamples)) in f64.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "ifb_internal.h"
+
+namespace ifb {
+
+namespace {
+
+constexpr int kStages = 2;
+
+struct ScoreStdParams {
+    const float *X;          // column-major matrix (fallback loader) -- also the TMA source
+    int64_t n_rows;
+    int64_t ld;
+    int32_t d;
+    int32_t box_d;           // features per TMA box (<= 256)
+    int32_t rem_d;           // features in the trailing partial box (0 = none)
+    const float *val;        // chunk tables in global memory
+    const uint32_t *meta;
+    const uint32_t *roots;   // byte offsets of the chunk's tree roots inside val[]
+    int32_t chunk_words;
+    int32_t n_trees;         // trees in this chunk
+    int32_t max_depth;
+    int32_t total_trees;     // ensemble size (divisor of the mean)
+    float avg_path;          // c(numSamples)
+    int32_t first_chunk;     // start sums at 0 instead of reading path_sum / depth_sum
+    int32_t finalize;        // write scores
+    double *scores;
+    float *path_sum;         // may be null when first_chunk && finalize
+    int32_t *depth_sum;      // may be null
+    int64_t n_tiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int32_t c0, int32_t c1,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], "
+        "[%4];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Shared-memory carve-up (byte offsets from the dynamic smem base, which is 1024-aligned).
+struct SmemLayout {
+    uint32_t bars;    // kStages mbarriers
+    uint32_t roots;   // n_trees u32
+    uint32_t val;     // chunk_words f32
+    uint32_t meta;    // chunk_words u32
+    uint32_t tiles;   // kStages * R * (d+1) f32, 128-byte aligned
+    uint32_t total;
+};
+__host__ __device__ inline SmemLayout make_layout(int n_trees, int chunk_words, int R, int d) {
+    SmemLayout L;
+    L.bars = 0;
+    L.roots = 64;
+    L.val = (L.roots + (uint32_t)n_trees * 4 + 15u) & ~15u;
+    L.meta = L.val + (uint32_t)chunk_words * 4;
+    L.tiles = (L.meta + (uint32_t)chunk_words * 4 + 127u) & ~127u;
+    L.total = L.tiles + (uint32_t)kStages * (uint32_t)R * (uint32_t)(d + 1) * 4u;
+    return L;
+}
+
+template <int R, int C, bool USE_TMA, bool WANT_DEPTH>
+__global__ void __launch_bounds__(R, 1)
+score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_rem,
+                 const ScoreStdParams p) {
+    constexpr int RB = R < 256 ? R : 256;  // rows per TMA box == row stride of the smem tile
+    constexpr int NSUB = R / RB;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, p.d);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+    const int tid = threadIdx.x;
+    const int d = p.d;
+    const uint32_t tile_floats = (uint32_t)R * (uint32_t)(d + 1);
+    const uint32_t sub_floats = (uint32_t)RB * (uint32_t)(d + 1);
+
+    // ---- one-time setup: barriers, forest chunk, NaN pseudo columns -------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        uint32_t *sroots = reinterpret_cast<uint32_t *>(smem + L.roots);
+        for (int i = tid; i < p.n_trees; i += R) sroots[i] = p.roots[i];
+        // val and meta are 16-byte aligned in both spaces (chunk starts are padded on the host)
+        float *sval = reinterpret_cast<float *>(smem + L.val);
+        uint32_t *smeta = reinterpret_cast<uint32_t *>(smem + L.meta);
+        for (int i = tid; i < p.chunk_words; i += R) {
+            sval[i] = p.val[i];
+            smeta[i] = p.meta[i];
+        }
+        float *tiles = reinterpret_cast<float *>(smem + L.tiles);
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int i = tid; i < kStages * NSUB * RB; i += R) {
+            const int s = i / (NSUB * RB), rem = i % (NSUB * RB);
+            const int sub = rem / RB, r = rem % RB;
+            tiles[(uint32_t)s * tile_floats + (uint32_t)sub * sub_floats + (uint32_t)d * RB + r] = qnan;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t tile_bytes = (uint32_t)R * (uint32_t)d * 4u;  // bytes one stage receives from TMA
+    auto issue_tile = [&](int64_t tile, int stage) {
+        // called by thread 0 only (TMA path)
+        float *dst = reinterpret_cast<float *>(smem + L.tiles) + (uint32_t)stage * tile_floats;
+        mbar_expect_tx(&bars[stage], tile_bytes);
+        const int64_t row0 = tile * R;
+#pragma unroll
+        for (int sub = 0; sub < NSUB; sub++) {
+            float *sdst = dst + (uint32_t)sub * sub_floats;
+            const int32_t r0 = (int32_t)(row0 + (int64_t)sub * RB);
+            int f = 0;
+            for (; f + p.box_d <= d; f += p.box_d) tma_load_2d(sdst + (uint32_t)f * RB, &tmap_main, r0, f, &bars[stage]);
+            if (p.rem_d) tma_load_2d(sdst + (uint32_t)f * RB, &tmap_rem, r0, f, &bars[stage]);
+        }
+    };
+    auto load_tile_plain = [&](int64_t tile, int stage) {
+        // all threads; column-major source: lanes run along rows => coalesced
+        float *dst = reinterpret_cast<float *>(smem + L.tiles) + (uint32_t)stage * tile_floats;
+        const int64_t row0 = tile * R;
+        const int sub = tid / RB, r = tid % RB;
+        const int64_t row = row0 + tid;
+        float *sdst = dst + (uint32_t)sub * sub_floats + r;
+        if (row < p.n_rows) {
+            const float *src = p.X + row;
+#pragma unroll 4
+            for (int f = 0; f < d; f++) sdst[(uint32_t)f * RB] = __ldg(src + (int64_t)f * p.ld);
+        } else {
+            for (int f = 0; f < d; f++) sdst[(uint32_t)f * RB] = 0.f;
+        }
+    };
+
+    int64_t tile = blockIdx.x;
+    const int64_t stride = gridDim.x;
+    if constexpr (USE_TMA) {
+        if (tid == 0) {
+            if (tile < p.n_tiles) issue_tile(tile, 0);
+            if (tile + stride < p.n_tiles) issue_tile(tile + stride, 1);
+        }
+    }
+
+    const unsigned char *sbase = smem;
+    const uint32_t val_off = L.val, meta_off = L.meta;
+    const uint32_t *sroots = reinterpret_cast<const uint32_t *>(smem + L.roots);
+    const int sub = tid / RB, rl = tid % RB;
+    const int n_trees = p.n_trees;
+    const int max_depth = p.max_depth;
+
+    for (int64_t k = 0; tile < p.n_tiles; tile += stride, ++k) {
+        const int stage = (int)(k & 1);
+        if constexpr (USE_TMA) {
+            mbar_wait(&bars[stage], (uint32_t)((k >> 1) & 1));
+        } else {
+            load_tile_plain(tile, stage);
+            __syncthreads();
+        }
+        const unsigned char *xrow = smem + L.tiles +
+                                    ((uint32_t)stage * tile_floats + (uint32_t)sub * sub_floats + (uint32_t)rl) * 4u;
+        const int64_t row = tile * R + tid;
+        const bool live = row < p.n_rows;
+
+        float s = 0.f;
+        int32_t dsum = 0;
+        if (!p.first_chunk && live) {
+            s = p.path_sum[row];
+            if (WANT_DEPTH) dsum = p.depth_sum[row];
+        }
+
+        int t = 0;
+        for (; t + C <= n_trees; t += C) {
+            uint32_t node[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) node[c] = sroots[t + c];
+#pragma unroll 1
+            for (int lvl = 0; lvl < max_depth; lvl++) {
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    const float v = *reinterpret_cast<const float *>(sbase + val_off + node[c]);
+                    const uint32_t m = *reinterpret_cast<const uint32_t *>(sbase + meta_off + node[c]);
+                    const uint32_t feat = m >> 20;
+                    const float x = *reinterpret_cast<const float *>(xrow + feat * (uint32_t)(RB * 4));
+                    if (WANT_DEPTH) dsum += (feat != (uint32_t)d) ? 1 : 0;
+                    node[c] = (m & 0xFFFFFu) + ((x < v) ? 0u : 4u);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; c++) s = s + *reinterpret_cast<const float *>(sbase + val_off + node[c]);
+        }
+        for (; t < n_trees; t++) {
+            uint32_t node = sroots[t];
+#pragma unroll 1
+            for (int lvl = 0; lvl < max_depth; lvl++) {
+                const float v = *reinterpret_cast<const float *>(sbase + val_off + node);
+                const uint32_t m = *reinterpret_cast<const uint32_t *>(sbase + meta_off + node);
+                const uint32_t feat = m >> 20;
+                const float x = *reinterpret_cast<const float *>(xrow + feat * (uint32_t)(RB * 4));
+                if (WANT_DEPTH) dsum += (feat != (uint32_t)d) ? 1 : 0;
+                node = (m & 0xFFFFFu) + ((x < v) ? 0u : 4u);
+            }
+            s = s + *reinterpret_cast<const float *>(sbase + val_off + node);
+        }
+
+        if (live) {
+            if (p.finalize) {
+                // IF/IsolationForestModel.scala:137-138: Float sum / Int, -Float / Float, Math.pow(2, Double)
+                const float e = __fdiv_rn(s, (float)p.total_trees);
+                const float z = __fdiv_rn(-e, p.avg_path);
+                p.scores[row] = exp2((double)z);
+            }
+            if (p.path_sum) p.path_sum[row] = s;
+            if (WANT_DEPTH) p.depth_sum[row] = dsum;
+        }
+        __syncthreads();  // every read of this stage is done before it is refilled
+        if constexpr (USE_TMA) {
+            if (tid == 0 && tile + 2 * stride < p.n_tiles) issue_tile(tile + 2 * stride, stage);
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+int make_tmap(CUtensorMap *map, const float *X, int64_t n_rows, int32_t d, int64_t ld, int box_rows, int box_d) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return IFB_ECUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)n_rows, (cuuint64_t)d};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_d};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(X), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (n_rows=%lld d=%d ld=%lld box=%dx%d)", (int)r,
+                  (long long)n_rows, d, (long long)ld, box_rows, box_d);
+        return IFB_ECUDA;
+    }
+    return IFB_OK;
+}
+
+template <int R, int C>
+int launch_variant(bool use_tma, bool want_depth, const CUtensorMap &m0, const CUtensorMap &m1,
+                   const ScoreStdParams &p, int grid, size_t smem, cudaStream_t stream) {
+    auto go = [&](auto kern) -> int {
+        IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, R, smem, stream>>>(m0, m1, p);
+        IFB_CUDA(cudaGetLastError());
+        count_launch();
+        return IFB_OK;
+    };
+    if (use_tma)
+        return want_depth ? go(score_std_kernel<R, C, true, true>) : go(score_std_kernel<R, C, true, false>);
+    return want_depth ? go(score_std_kernel<R, C, false, true>) : go(score_std_kernel<R, C, false, false>);
+}
+
+}  // namespace
+
+int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const float *X, int64_t n_rows, int32_t d,
+                          int64_t ld, int32_t layout, double *scores, int32_t *depth_sum, float *path_sum,
+                          bool accumulate_only, cudaStream_t stream) {
+    IFB_REQUIRE(layout == IFB_COL_MAJOR, "launch_score_standard expects a column-major matrix");
+    if (n_rows == 0) return IFB_OK;
+    const int R = plan->rows_per_tile;
+    const int RB = R < 256 ? R : 256;
+    const bool want_depth = depth_sum != nullptr;
+    const size_t n_chunks = plan->chunks.size();
+    IFB_REQUIRE(n_chunks <= 1 || path_sum != nullptr || accumulate_only,
+                "internal: multi-chunk scoring needs a path_sum scratch buffer");
+
+    // TMA needs a 16-byte aligned base and a row pitch that is a multiple of 16 bytes
+    bool use_tma = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (ld % 4 == 0) && n_rows < (1LL << 31);
+    CUtensorMap m0, m1;
+    std::memset(&m0, 0, sizeof m0);
+    std::memset(&m1, 0, sizeof m1);
+    const int box_d = std::min(d, 256);
+    const int rem_d = d % box_d;
+    if (use_tma) {
+        int rc = make_tmap(&m0, X, n_rows, d, ld, RB, box_d);
+        if (rc) return rc;
+        if (rem_d) {
+            rc = make_tmap(&m1, X, n_rows, d, ld, RB, rem_d);
+            if (rc) return rc;
+        } else {
+            m1 = m0;
+        }
+    }
+    const int sms = device_sm_count(f->device);
+    const int64_t n_tiles = (n_rows + R - 1) / R;
+    const int grid = (int)std::min<int64_t>(n_tiles, sms);
+
+    for (size_t ci = 0; ci < n_chunks; ci++) {
+        const StdChunk &c = plan->chunks[ci];
+        ScoreStdParams p;
+        p.X = X;
+        p.n_rows = n_rows;
+        p.ld = ld;
+        p.d = d;
+        p.box_d = box_d;
+        p.rem_d = rem_d;
+        p.val = plan->d_val + c.node_begin;
+        p.meta = plan->d_meta + c.node_begin;
+        p.roots = plan->d_tree_root + c.tree_begin;
+        p.chunk_words = c.node_count;
+        p.n_trees = c.tree_end - c.tree_begin;
+        p.max_depth = f->max_depth;
+        p.total_trees = f->num_trees;
+        p.avg_path = f->avg_path_norm;
+        p.first_chunk = (ci == 0 && !accumulate_only) ? 1 : 0;
+        p.finalize = (ci + 1 == n_chunks && !accumulate_only) ? 1 : 0;
+        p.scores = scores;
+        p.path_sum = path_sum;
+        p.depth_sum = depth_sum;
+        p.n_tiles = n_tiles;
+        const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, d);
+        int rc;
+        switch (R) {
+            case 512: rc = launch_variant<512, 2>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
+            case 256: rc = launch_variant<256, 4>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
+            case 128: rc = launch_variant<128, 8>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
+            case 64: rc = launch_variant<64, 8>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
+            default: rc = launch_variant<32, 8>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
+        }
+        if (rc) return rc;
+    }
+    return IFB_OK;
+}
+
+}  // namespace ifb
