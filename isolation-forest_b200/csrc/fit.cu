@@ -1,6 +1,764 @@
-// placeholder, replaced below
+// Tree building for sm_100a: one launch builds every tree of a forest shard, one CTA per tree.
+//
+// Replaces IsolationTree.fit / generateIsolationTree (IF/IsolationTree.scala:53-183),
+// ExtendedIsolationTree.fit / generateExtendedIsolationTree (IF/extended/ExtendedIsolationTree.scala:67-270)
+// and the per-tree setup of trainIsolationTrees (IF/core/SharedTrainLogic.scala:276-317).
+//
+// Determinism contract (DESIGN.md "fit"): a tree is a pure function of (randomSeed, numPartitions, tree id,
+// data).  Thread 0 of the CTA owns the tree's java.util.Random stream (48-bit LCG, nextInt/nextDouble/
+// nextGaussian exactly as the JDK specifies, StrictMath.log restated from fdlibm) and consumes it in the
+// reference's order: node by node in PRE-ORDER (the recursion order of the Scala code), so the node tables
+// come out in the persisted pre-order layout.  All data-parallel work of a node (feature min/max, the
+// hyperplane dot products, the partition of the node's row list) is spread over the CTA's threads with
+// warp-shuffle reductions and ballot/popc scans.  This translation unit is compiled with -fmad=false:
+// the JVM never contracts a*b+c, so neither may the f64 split arithmetic here.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "ifb_internal.h"
-extern "C" {
-int ifb_fit_device(int32_t, const float *, int64_t, int32_t, int64_t, int32_t, const ifb_fit_params *, ifb_forest **, void *) { ifb::set_error("fit not built"); return IFB_ESTATE; }
-int ifb_fit_host(int32_t, const float *, int64_t, int32_t, int64_t, int32_t, const ifb_fit_params *, ifb_forest **) { ifb::set_error("fit not built"); return IFB_ESTATE; }
+
+namespace ifb {
+namespace {
+
+constexpr int BT = 256;  // threads per CTA (one CTA builds one tree)
+
+struct FitDev {
+    const float *X;
+    int64_t N, ld;
+    int32_t d, layout;
+    int32_t n, num_features, bootstrap;
+    int64_t random_seed;
+    int32_t num_partitions, ext_level, k;
+    int32_t tree_begin, height_limit, cap, cap_internal;
+    // outputs (per tree at stride cap / cap_internal)
+    int32_t *n_nodes, *n_internal;
+    int32_t *left, *right;
+    int64_t *num_instances;
+    int32_t *feature;
+    double *threshold;
+    double *offset;
+    int32_t *hp_slot;
+    int32_t *hp_idx;
+    float *hp_w;
+    int64_t *rows;  // [trees][n] sampled row ids
+    // scratch (per tree)
+    int32_t *perm, *perm2;       // [n]
+    int64_t *hkeys, *hvals;      // [hcap]
+    int32_t hcap;
+    int32_t *feat_perm;          // [d]
+    int32_t *feat_idx;           // [num_features] sorted feature subset
+    int32_t *avail;              // [num_features]
+    int32_t *e_idx;              // [k]
+    double *e_raw;               // [k]
+    float *e_w, *e_mn, *e_mx;    // [k]
+};
+
+// ---- java.util.Random ---------------------------------------------------------------------------
+struct JRandom {
+    unsigned long long seed;
+    int have_next;
+    double next_gauss;
+};
+__device__ __forceinline__ void jr_init(JRandom &r, long long seed) {
+    r.seed = ((unsigned long long)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
+    r.have_next = 0;
+    r.next_gauss = 0.0;
+}
+__device__ __forceinline__ int jr_next(JRandom &r, int bits) {
+    r.seed = (r.seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int)(long long)(r.seed >> (48 - bits));
+}
+__device__ int jr_next_int(JRandom &r, int bound) {
+    int rr = jr_next(r, 31);
+    const int m = bound - 1;
+    if ((bound & m) == 0) return (int)(((long long)bound * (long long)rr) >> 31);
+    for (int u = rr;; u = jr_next(r, 31)) {
+        rr = u % bound;
+        if ((int)((unsigned)u - (unsigned)rr + (unsigned)m) >= 0) break;
+    }
+    return rr;
+}
+__device__ __forceinline__ double jr_next_double(JRandom &r) {
+    const long long hi = (long long)jr_next(r, 26);
+    const long long lo = (long long)jr_next(r, 27);
+    return (double)((hi << 27) + lo) * 0x1.0p-53;
+}
+__device__ long long jr_bounded(JRandom &r, long long m) {
+    if (m < 0x7fffffffLL) return jr_next_int(r, (int)m);
+    const unsigned long long hi = (unsigned long long)jr_next(r, 31), lo = (unsigned long long)jr_next(r, 31);
+    return (long long)(((hi << 31) | lo) % (unsigned long long)m);
+}
+
+// StrictMath.log: fdlibm __ieee754_log (public algorithm).  No FMA contraction (-fmad=false).
+__device__ double fdlibm_log(double x) {
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                 two54 = 1.80143985094819840000e+16, Lg1 = 6.666666666666735130e-01,
+                 Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01, Lg7 = 1.479819860511658591e-01;
+    int hx = __double2hiint(x);
+    unsigned lx = (unsigned)__double2loint(x);
+    int k = 0, i, j;
+    double hfsq, f, s, z, R, w, t1, t2, dk;
+    if (hx < 0x00100000) {
+        if (((hx & 0x7fffffff) | lx) == 0) return -INFINITY;
+        if (hx < 0) return NAN;
+        k -= 54;
+        x *= two54;
+        hx = __double2hiint(x);
+        lx = (unsigned)__double2loint(x);
+    }
+    if (hx >= 0x7ff00000) return x + x;
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    i = (hx + 0x95f64) & 0x100000;
+    x = __hiloint2double(hx | (i ^ 0x3ff00000), (int)lx);
+    k += (i >> 20);
+    f = x - 1.0;
+    if ((0x000fffff & (2 + hx)) < 3) {
+        if (f == 0.0) {
+            if (k == 0) return 0.0;
+            dk = (double)k;
+            return dk * ln2_hi + dk * ln2_lo;
+        }
+        R = f * f * (0.5 - 0.33333333333333333 * f);
+        if (k == 0) return f - R;
+        dk = (double)k;
+        return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+    }
+    s = f / (2.0 + f);
+    dk = (double)k;
+    z = s * s;
+    i = hx - 0x6147a;
+    w = z * z;
+    j = 0x6b851 - hx;
+    t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    i |= j;
+    R = t2 + t1;
+    if (i > 0) {
+        hfsq = 0.5 * f * f;
+        if (k == 0) return f - (hfsq - s * (hfsq + R));
+        return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+    }
+    if (k == 0) return f - s * (f - R);
+    return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+
+__device__ double jr_next_gaussian(JRandom &r) {
+    if (r.have_next) {
+        r.have_next = 0;
+        return r.next_gauss;
+    }
+    double v1, v2, s;
+    do {
+        v1 = 2 * jr_next_double(r) - 1;
+        v2 = 2 * jr_next_double(r) - 1;
+        s = v1 * v1 + v2 * v2;
+    } while (s >= 1 || s == 0);
+    const double multiplier = sqrt(-2 * fdlibm_log(s) / s);
+    r.next_gauss = v2 * multiplier;
+    r.have_next = 1;
+    return v1 * multiplier;
+}
+
+// scala.util.Random.shuffle on an int array: for (n <- len to 2 by -1) swap(n-1, nextInt(n))
+__device__ void scala_shuffle(JRandom &r, int32_t *a, int len) {
+    for (int n = len; n >= 2; n--) {
+        const int kk = jr_next_int(r, n);
+        const int32_t tmp = a[n - 1];
+        a[n - 1] = a[kk];
+        a[kk] = tmp;
+    }
+}
+
+__device__ __forceinline__ float feat_value(const FitDev &p, long long row, int f) {
+    return p.layout == IFB_COL_MAJOR ? __ldg(p.X + (long long)f * p.ld + row) : __ldg(p.X + row * p.ld + f);
+}
+
+struct NodeTask {
+    int32_t start, count, height, parent, is_right;
+};
+
+struct Shared {
+    NodeTask cur;
+    int32_t done, id, trial, found, leaf, nl;
+    int32_t feature;
+    double split;
+    float red_mn[BT / 32], red_mx[BT / 32];
+    int32_t warp_l[BT / 32], warp_r[BT / 32];
+    int32_t base_l, base_r;
+    int32_t nnz, slot;
+    double offset;
+    NodeTask stack[72];
+};
+
+// block-wide min/max of feature f over rows perm[start .. start+count)
+__device__ void block_min_max(const FitDev &p, Shared &sh, const int32_t *perm, const int64_t *rows, int start,
+                              int count, int f, float &mn_out, float &mx_out) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < count; i += BT) {
+        const float v = feat_value(p, rows[perm[start + i]], f);
+        // Scala's `if (v < mn) mn = v; if (v > mx) mx = v` (NaN never replaces)
+        if (v < mn) mn = v;
+        if (v > mx) mx = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        if (a < mn) mn = a;
+        if (b > mx) mx = b;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        sh.red_mn[threadIdx.x >> 5] = mn;
+        sh.red_mx[threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    mn = sh.red_mn[0];
+    mx = sh.red_mx[0];
+#pragma unroll
+    for (int w = 1; w < BT / 32; w++) {
+        if (sh.red_mn[w] < mn) mn = sh.red_mn[w];
+        if (sh.red_mx[w] > mx) mx = sh.red_mx[w];
+    }
+    mn_out = mn;
+    mx_out = mx;
+}
+
+// Partition perm[start..start+count) so that rows with go_left come first; returns the left count in sh.nl.
+// Order inside the halves is irrelevant to the algorithm (only min/max and sizes are ever taken).
+template <typename Pred>
+__device__ void block_partition(Shared &sh, int32_t *perm, int32_t *perm2, int start, int count, Pred go_left) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        sh.base_l = 0;
+        sh.base_r = 0;
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < count; c0 += BT) {
+        const int i = c0 + threadIdx.x;
+        const bool valid = i < count;
+        const int32_t pr = valid ? perm[start + i] : 0;
+        const bool l = valid && go_left(pr);
+        const bool r = valid && !l;
+        const unsigned bl = __ballot_sync(0xffffffffu, l), br = __ballot_sync(0xffffffffu, r);
+        if (lane == 0) {
+            sh.warp_l[warp] = __popc(bl);
+            sh.warp_r[warp] = __popc(br);
+        }
+        __syncthreads();
+        int off_l = sh.base_l, off_r = sh.base_r, tot_l = 0, tot_r = 0;
+#pragma unroll
+        for (int w = 0; w < BT / 32; w++) {
+            if (w < warp) {
+                off_l += sh.warp_l[w];
+                off_r += sh.warp_r[w];
+            }
+            tot_l += sh.warp_l[w];
+            tot_r += sh.warp_r[w];
+        }
+        const unsigned below = (1u << lane) - 1u;
+        if (l) perm2[start + off_l + __popc(bl & below)] = pr;
+        if (r) perm2[start + count - 1 - (off_r + __popc(br & below))] = pr;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sh.base_l += tot_l;
+            sh.base_r += tot_r;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < count; i += BT) perm[start + i] = perm2[start + i];
+    if (threadIdx.x == 0) sh.nl = sh.base_l;
+    __syncthreads();
+}
+
+template <bool EXT>
+__global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
+    __shared__ Shared sh;
+    const int tl = blockIdx.x;                 // tree index inside the shard
+    const int tid = threadIdx.x;
+    const long long tree_id = (long long)p.tree_begin + tl;
+    // treeSeed = randomSeed + 2*(P+1) + treeId  (IF/IsolationForest.scala:76-78, SharedTrainLogic.scala:283)
+    const long long tree_seed = p.random_seed + 2LL * ((long long)p.num_partitions + 1) + tree_id;
+
+    int64_t *rows = p.rows + (int64_t)tl * p.n;
+    int32_t *perm = p.perm + (int64_t)tl * p.n, *perm2 = p.perm2 + (int64_t)tl * p.n;
+    int64_t *hkeys = p.hkeys + (int64_t)tl * p.hcap, *hvals = p.hvals + (int64_t)tl * p.hcap;
+    int32_t *feat_perm = p.feat_perm + (int64_t)tl * p.d;
+    int32_t *feat_idx = p.feat_idx + (int64_t)tl * p.num_features;
+    int32_t *avail = p.avail + (int64_t)tl * p.num_features;
+    int32_t *o_left = p.left + (int64_t)tl * p.cap, *o_right = p.right + (int64_t)tl * p.cap;
+    int64_t *o_ninst = p.num_instances + (int64_t)tl * p.cap;
+
+    // ---- per-tree sampling (engine-defined contract, DESIGN.md "fit: sampling") -------------------
+    for (int i = tid; i < p.hcap; i += BT) hkeys[i] = -1;
+    for (int i = tid; i < p.d; i += BT) feat_perm[i] = i;
+    for (int i = tid; i < p.n; i += BT) perm[i] = i;
+    __syncthreads();
+    JRandom rnd;
+    if (tid == 0) {
+        jr_init(rnd, tree_seed);
+        if (p.bootstrap) {
+            for (int i = 0; i < p.n; i++) rows[i] = jr_bounded(rnd, p.N);
+        } else {
+            const int mask = p.hcap - 1;
+            auto slot_of = [&](long long key) {
+                int s = (int)(((unsigned long long)key * 0x9E3779B97F4A7C15ULL) >> 40) & mask;
+                while (hkeys[s] != -1 && hkeys[s] != key) s = (s + 1) & mask;
+                return s;
+            };
+            for (int i = 0; i < p.n; i++) {
+                const long long j = (long long)i + jr_bounded(rnd, p.N - i);
+                int sj = slot_of(j);
+                const long long aj = hkeys[sj] == j ? hvals[sj] : j;
+                const int si = slot_of((long long)i);
+                const long long ai = hkeys[si] == (long long)i ? hvals[si] : (long long)i;
+                rows[i] = aj;
+                sj = slot_of(j);
+                hkeys[sj] = j;
+                hvals[sj] = ai;
+            }
+        }
+        // featureIndices = shuffle(0 until d).take(numFeatures).sorted   (SharedTrainLogic.scala:300-304)
+        scala_shuffle(rnd, feat_perm, p.d);
+        for (int a = 0; a < p.num_features; a++) feat_idx[a] = feat_perm[a];
+        for (int a = 1; a < p.num_features; a++) {
+            const int32_t kv = feat_idx[a];
+            int b = a - 1;
+            while (b >= 0 && feat_idx[b] > kv) {
+                feat_idx[b + 1] = feat_idx[b];
+                b--;
+            }
+            feat_idx[b + 1] = kv;
+        }
+        // the builder restarts from new Random(treeSeed)  (IF/IsolationTree.scala:63)
+        jr_init(rnd, tree_seed);
+        sh.stack[0] = NodeTask{0, p.n, 0, -1, 0};
+    }
+    __syncthreads();
+
+    int sp = 1;        // thread 0 only
+    int nnodes = 0;    // thread 0 only
+    int ninternal = 0; // thread 0 only
+
+    while (true) {
+        if (tid == 0) {
+            if (sp == 0) {
+                sh.done = 1;
+            } else {
+                sh.done = 0;
+                sh.cur = sh.stack[--sp];
+                sh.id = nnodes++;
+                if (sh.cur.is_right) o_right[sh.cur.parent] = sh.id;
+            }
+        }
+        __syncthreads();
+        if (sh.done) break;
+        const NodeTask cur = sh.cur;
+        const int id = sh.id;
+
+        if (!EXT) {
+            // getFeatureToSplit runs before the stop test and consumes draws (IF/IsolationTree.scala:124-156)
+            for (int i = tid; i < p.num_features; i += BT) avail[i] = feat_idx[i];
+            if (tid == 0) sh.found = 0;
+            __syncthreads();
+            int n_avail = p.num_features;  // replicated in every thread
+            while (true) {
+                if (tid == 0) {
+                    if (sh.found || n_avail == 0) {
+                        sh.trial = -1;
+                    } else {
+                        const int pick = jr_next_int(rnd, n_avail);
+                        sh.trial = avail[pick];
+                        for (int q = pick; q + 1 < n_avail; q++) avail[q] = avail[q + 1];  // ListBuffer.remove
+                    }
+                }
+                __syncthreads();
+                const int trial = sh.trial;
+                if (trial < 0) break;
+                n_avail--;
+                float mn = 0.f, mx = 0.f;
+                if (cur.count > 0) block_min_max(p, sh, perm, rows, cur.start, cur.count, trial, mn, mx);
+                if (tid == 0 && cur.count > 0) {
+                    const double dmn = (double)mn, dmx = (double)mx;
+                    if (dmn != dmx) {
+                        sh.found = 1;
+                        sh.feature = trial;
+                        sh.split = (dmx - dmn) * jr_next_double(rnd) + dmn;  // :145-146
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                sh.leaf = (!sh.found || cur.height >= p.height_limit || cur.count <= 1) ? 1 : 0;
+                int32_t *o_feat = p.feature + (int64_t)tl * p.cap;
+                double *o_thr = p.threshold + (int64_t)tl * p.cap;
+                if (sh.leaf) {
+                    o_left[id] = -1;
+                    o_right[id] = -1;
+                    o_feat[id] = -1;
+                    o_thr[id] = 0.0;
+                    o_ninst[id] = cur.count;
+                } else {
+                    o_left[id] = id + 1;
+                    o_feat[id] = sh.feature;
+                    o_thr[id] = sh.split;
+                    o_ninst[id] = -1;
+                }
+            }
+            __syncthreads();
+            if (sh.leaf) continue;
+            const int f = sh.feature;
+            const double split = sh.split;
+            // left = x < split (f32 widened, strict); everything else goes right.  (The reference filters
+            // right with x >= split, dropping NaN rows; NaN training features are outside the contract.)
+            block_partition(sh, perm, perm2, cur.start, cur.count,
+                            [&](int32_t pr) { return (double)feat_value(p, rows[pr], f) < split; });
+            if (tid == 0) {
+                const int nl = sh.nl;
+                sh.stack[sp++] = NodeTask{cur.start + nl, cur.count - nl, cur.height + 1, id, 1};
+                sh.stack[sp++] = NodeTask{cur.start, nl, cur.height + 1, id, 0};
+            }
+            __syncthreads();
+        } else {
+            // ---- extended: IF/extended/ExtendedIsolationTree.scala:139-260 -----------------------
+            double *o_off = p.offset + (int64_t)tl * p.cap;
+            int32_t *o_slot = p.hp_slot + (int64_t)tl * p.cap;
+            int32_t *e_idx = p.e_idx + (int64_t)tl * p.k;
+            double *e_raw = p.e_raw + (int64_t)tl * p.k;
+            float *e_w = p.e_w + (int64_t)tl * p.k, *e_mn = p.e_mn + (int64_t)tl * p.k, *e_mx = p.e_mx + (int64_t)tl * p.k;
+            const int dim = p.num_features;
+            const int nnz = p.k;  // min(extensionLevel + 1, dim)
+            if (tid == 0) sh.leaf = (cur.height >= p.height_limit || cur.count <= 1) ? 1 : 0;  // :152-153
+            __syncthreads();
+            if (!sh.leaf) {
+                for (int i = tid; i < dim; i += BT) feat_perm[i] = i;
+                __syncthreads();
+                if (tid == 0) {
+                    scala_shuffle(rnd, feat_perm, dim);                                   // :160
+                    for (int i = 0; i < nnz; i++) {
+                        e_idx[i] = feat_idx[feat_perm[i]];                                // :168
+                        e_raw[i] = jr_next_gaussian(rnd);                                 // :169
+                    }
+                    double sq = 0.0;
+                    for (int i = 0; i < nnz; i++) sq += e_raw[i] * e_raw[i];              // :174-179
+                    const double norm = sqrt(sq);
+                    if (norm == 0) {
+                        sh.leaf = 1;                                                      // :183-184
+                    } else {
+                        for (int i = 0; i < nnz; i++) e_w[i] = (float)(e_raw[i] / norm);  // :190-195
+                    }
+                }
+                __syncthreads();
+            }
+            if (sh.leaf) {
+                if (tid == 0) {
+                    o_left[id] = -1;
+                    o_right[id] = -1;
+                    o_off[id] = 0.0;
+                    o_slot[id] = -1;
+                    o_ninst[id] = cur.count;
+                }
+                __syncthreads();
+                continue;
+            }
+            // per-coordinate min/max over the node's rows: one warp per coordinate, lanes along rows
+            {
+                const int lane = tid & 31, warp = tid >> 5;
+                for (int kk = warp; kk < nnz; kk += BT / 32) {
+                    const int j = e_idx[kk];
+                    float mn = INFINITY, mx = -INFINITY;
+                    for (int i = lane; i < cur.count; i += 32) {
+                        const float v = feat_value(p, rows[perm[cur.start + i]], j);
+                        if (v < mn) mn = v;
+                        if (v > mx) mx = v;
+                    }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+                        if (a < mn) mn = a;
+                        if (b > mx) mx = b;
+                    }
+                    if (lane == 0) {
+                        e_mn[kk] = mn;
+                        e_mx[kk] = mx;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double off = 0.0;
+                for (int kk = 0; kk < nnz; kk++) {                                        // :201-217
+                    const double mn = (double)e_mn[kk], mx = (double)e_mx[kk];
+                    const double iv = (mn == mx) ? mn : mn + jr_next_double(rnd) * (mx - mn);
+                    off += (double)e_w[kk] * iv;
+                }
+                sh.offset = off;
+                sh.slot = ninternal++;
+                o_left[id] = id + 1;
+                o_off[id] = off;
+                o_slot[id] = sh.slot;
+                o_ninst[id] = -1;
+            }
+            __syncthreads();
+            // canonical order (:220-226): rank of each chosen index among the chosen indices
+            int32_t *h_idx = p.hp_idx + ((int64_t)tl * p.cap_internal + sh.slot) * p.k;
+            float *h_w = p.hp_w + ((int64_t)tl * p.cap_internal + sh.slot) * p.k;
+            for (int i = tid; i < nnz; i += BT) {
+                const int32_t me = e_idx[i];
+                int rank = 0;
+                for (int q = 0; q < nnz; q++) rank += (e_idx[q] < me) ? 1 : 0;
+                h_idx[rank] = me;
+                h_w[rank] = e_w[i];
+            }
+            __syncthreads();
+            const double off = sh.offset;
+            block_partition(sh, perm, perm2, cur.start, cur.count, [&](int32_t pr) {      // :230-232
+                const long long row = rows[pr];
+                double sum = 0.0;
+                for (int q = 0; q < nnz; q++) {
+                    const float prod = __fmul_rn(h_w[q], feat_value(p, row, h_idx[q]));
+                    sum = sum + (double)prod;
+                }
+                return sum < off;
+            });
+            if (tid == 0) {
+                const int nl = sh.nl;
+                sh.stack[sp++] = NodeTask{cur.start + nl, cur.count - nl, cur.height + 1, id, 1};
+                sh.stack[sp++] = NodeTask{cur.start, nl, cur.height + 1, id, 0};
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        p.n_nodes[tl] = nnodes;
+        if (EXT) p.n_internal[tl] = ninternal;
+    }
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    cudaStream_t s;
+    explicit DevBuf(cudaStream_t st) : s(st) {}
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, s);
+        if (e != cudaSuccess) {
+            set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? IFB_ENOMEM : IFB_ECUDA;
+        }
+        return IFB_OK;
+    }
+    template <typename T>
+    T *as() { return reinterpret_cast<T *>(p); }
+};
+
+// heightLimit = ceil(log10(n)/log10(2))  (IF/IsolationTree.scala:60-61)
+int height_limit_of(int32_t n) { return (int)std::ceil(std::log10((double)n) / std::log10(2.0)); }
+
+}  // namespace
+}  // namespace ifb
+
+using namespace ifb;
+
+extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
+                              const ifb_fit_params *prm, ifb_forest **out, void *stream_) {
+    IFB_REQUIRE(out, "out is null");
+    *out = nullptr;
+    IFB_REQUIRE(prm && X, "null argument");
+    IFB_REQUIRE(layout == IFB_COL_MAJOR || layout == IFB_ROW_MAJOR, "unknown layout %d", layout);
+    IFB_REQUIRE(d >= 1 && n_rows >= 1, "empty training matrix");
+    IFB_REQUIRE(layout == IFB_COL_MAJOR ? ld >= n_rows : ld >= d, "leading dimension %lld too small", (long long)ld);
+    IFB_REQUIRE(prm->num_estimators > 0, "parameter numEstimators must be > 0, got %d", prm->num_estimators);
+    // messages of validateAndResolveParams (IF/core/SharedTrainLogic.scala:43-75)
+    IFB_REQUIRE(prm->num_features > 0, "parameter maxFeatures specifying the use of %d features, but >0 features are required.",
+                prm->num_features);
+    IFB_REQUIRE(prm->num_features <= d, "parameter maxFeatures specifying the use of %d features, but only %d features are available.",
+                prm->num_features, d);
+    IFB_REQUIRE(prm->num_samples >= 2, "parameter maxSamples specifying the use of %d samples, but >=2 samples are required.",
+                prm->num_samples);
+    IFB_REQUIRE((int64_t)prm->num_samples <= n_rows,
+                "parameter maxSamples specifying the use of %d samples, but only %lld samples are in the input dataset.",
+                prm->num_samples, (long long)n_rows);
+    IFB_REQUIRE(prm->num_samples <= (1 << 20), "numSamples %d exceeds the device builder's limit of 1048576", prm->num_samples);
+    const bool ext = prm->extension_level >= 0;
+    // IF/extended/ExtendedIsolationForest.scala:57-68
+    IFB_REQUIRE(!ext || prm->extension_level <= prm->num_features - 1,
+                "parameter extensionLevel given invalid value %d, but must be in [0, %d] for a subspace of %d features.",
+                prm->extension_level, prm->num_features - 1, prm->num_features);
+    int32_t tb = prm->tree_begin, te = prm->tree_end;
+    if (tb == 0 && te == 0) te = prm->num_estimators;
+    IFB_REQUIRE(0 <= tb && tb <= te && te <= prm->num_estimators, "tree shard [%d,%d) outside [0,%d)", tb, te,
+                prm->num_estimators);
+    const int ntrees = te - tb;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available; this engine has no CPU fallback");
+        return IFB_ENOGPU;
+    }
+    IFB_REQUIRE(device >= 0 && device < ndev, "device %d out of range", device);
+    DeviceGuard dg(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    const int n = prm->num_samples;
+    const int hl = height_limit_of(n);
+    IFB_REQUIRE(hl <= 32, "height limit %d too large", hl);
+    const int k = ext ? std::min(prm->extension_level + 1, prm->num_features) : 1;
+    // node capacity: standard trees have <= 2n-1 nodes; extended trees may keep empty leaves, bound by the
+    // complete tree of height hl, but never more than 2*internal+1 with internal <= min(2^hl - 1, ...)
+    int64_t cap = ext ? std::min<int64_t>((1LL << (hl + 1)) - 1, 4LL * n + 1) : 2LL * n - 1;
+    int64_t cap_internal = ext ? std::min<int64_t>((1LL << hl) - 1, 2LL * n) : 0;
+    if (ext) cap = std::min<int64_t>(cap, 2 * cap_internal + 1);
+    int hcap = 1;
+    while (hcap < 4 * n) hcap <<= 1;
+
+    FitDev p;
+    std::memset(&p, 0, sizeof p);
+    p.X = X; p.N = n_rows; p.ld = ld; p.d = d; p.layout = layout;
+    p.n = n; p.num_features = prm->num_features; p.bootstrap = prm->bootstrap ? 1 : 0;
+    p.random_seed = prm->random_seed; p.num_partitions = prm->num_partitions; p.ext_level = prm->extension_level;
+    p.k = k; p.tree_begin = tb; p.height_limit = hl; p.cap = (int32_t)cap; p.cap_internal = (int32_t)cap_internal;
+    p.hcap = hcap;
+
+    DevBuf b_nn(stream), b_ni(stream), b_left(stream), b_right(stream), b_ninst(stream), b_feat(stream), b_thr(stream),
+        b_off(stream), b_slot(stream), b_hidx(stream), b_hw(stream), b_rows(stream), b_perm(stream), b_perm2(stream),
+        b_hk(stream), b_hv(stream), b_fperm(stream), b_fidx(stream), b_avail(stream), b_eidx(stream), b_eraw(stream),
+        b_ew(stream), b_emn(stream), b_emx(stream);
+    int rc;
+    const size_t T = (size_t)std::max(ntrees, 1);
+#define ALLOC(buf, bytes)                     \
+    if ((rc = (buf).alloc(bytes))) return rc;
+    ALLOC(b_nn, T * 4) ALLOC(b_ni, T * 4) ALLOC(b_left, T * cap * 4) ALLOC(b_right, T * cap * 4)
+    ALLOC(b_ninst, T * cap * 8) ALLOC(b_rows, T * n * 8) ALLOC(b_perm, T * n * 4) ALLOC(b_perm2, T * n * 4)
+    ALLOC(b_hk, T * hcap * 8) ALLOC(b_hv, T * hcap * 8) ALLOC(b_fperm, T * d * 4)
+    ALLOC(b_fidx, T * prm->num_features * 4) ALLOC(b_avail, T * prm->num_features * 4)
+    if (ext) {
+        ALLOC(b_off, T * cap * 8) ALLOC(b_slot, T * cap * 4) ALLOC(b_hidx, T * cap_internal * k * 4)
+        ALLOC(b_hw, T * cap_internal * k * 4) ALLOC(b_eidx, T * k * 4) ALLOC(b_eraw, T * k * 8) ALLOC(b_ew, T * k * 4)
+        ALLOC(b_emn, T * k * 4) ALLOC(b_emx, T * k * 4)
+    } else {
+        ALLOC(b_feat, T * cap * 4) ALLOC(b_thr, T * cap * 8)
+    }
+#undef ALLOC
+    p.n_nodes = b_nn.as<int32_t>(); p.n_internal = b_ni.as<int32_t>();
+    p.left = b_left.as<int32_t>(); p.right = b_right.as<int32_t>(); p.num_instances = b_ninst.as<int64_t>();
+    p.feature = b_feat.as<int32_t>(); p.threshold = b_thr.as<double>();
+    p.offset = b_off.as<double>(); p.hp_slot = b_slot.as<int32_t>(); p.hp_idx = b_hidx.as<int32_t>(); p.hp_w = b_hw.as<float>();
+    p.rows = b_rows.as<int64_t>(); p.perm = b_perm.as<int32_t>(); p.perm2 = b_perm2.as<int32_t>();
+    p.hkeys = b_hk.as<int64_t>(); p.hvals = b_hv.as<int64_t>();
+    p.feat_perm = b_fperm.as<int32_t>(); p.feat_idx = b_fidx.as<int32_t>(); p.avail = b_avail.as<int32_t>();
+    p.e_idx = b_eidx.as<int32_t>(); p.e_raw = b_eraw.as<double>(); p.e_w = b_ew.as<float>();
+    p.e_mn = b_emn.as<float>(); p.e_mx = b_emx.as<float>();
+
+    if (ntrees > 0) {
+        if (ext) fit_kernel<true><<<ntrees, BT, 0, stream>>>(p);
+        else fit_kernel<false><<<ntrees, BT, 0, stream>>>(p);
+        IFB_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    // node tables back to the host, compacted into the persisted layout
+    std::vector<int32_t> n_nodes(T), n_int(T), left(T * cap), right(T * cap), feature, slot;
+    std::vector<int64_t> ninst(T * cap);
+    std::vector<double> thr, off;
+    IFB_CUDA(cudaMemcpyAsync(n_nodes.data(), p.n_nodes, T * 4, cudaMemcpyDeviceToHost, stream));
+    IFB_CUDA(cudaMemcpyAsync(left.data(), p.left, T * cap * 4, cudaMemcpyDeviceToHost, stream));
+    IFB_CUDA(cudaMemcpyAsync(right.data(), p.right, T * cap * 4, cudaMemcpyDeviceToHost, stream));
+    IFB_CUDA(cudaMemcpyAsync(ninst.data(), p.num_instances, T * cap * 8, cudaMemcpyDeviceToHost, stream));
+    if (ext) {
+        off.resize(T * cap);
+        slot.resize(T * cap);
+        IFB_CUDA(cudaMemcpyAsync(n_int.data(), p.n_internal, T * 4, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaMemcpyAsync(off.data(), p.offset, T * cap * 8, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaMemcpyAsync(slot.data(), p.hp_slot, T * cap * 4, cudaMemcpyDeviceToHost, stream));
+    } else {
+        feature.resize(T * cap);
+        thr.resize(T * cap);
+        IFB_CUDA(cudaMemcpyAsync(feature.data(), p.feature, T * cap * 4, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaMemcpyAsync(thr.data(), p.threshold, T * cap * 8, cudaMemcpyDeviceToHost, stream));
+    }
+    IFB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<int32_t> node_off(ntrees + 1, 0);
+    for (int t = 0; t < ntrees; t++) {
+        if (n_nodes[t] < 1 || n_nodes[t] > cap) {
+            set_error("internal: tree %d produced %d nodes (capacity %lld)", tb + t, n_nodes[t], (long long)cap);
+            return IFB_ESTATE;
+        }
+        node_off[t + 1] = node_off[t] + n_nodes[t];
+    }
+    const int64_t total = node_off[ntrees];
+    std::vector<int32_t> c_left(total), c_right(total), c_feat;
+    std::vector<int64_t> c_ninst(total);
+    std::vector<double> c_thr, c_off;
+    std::vector<int64_t> hp_off;
+    std::vector<int32_t> hp_idx;
+    std::vector<float> hp_w;
+    if (ext) {
+        c_off.resize(total);
+        hp_off.assign(total + 1, 0);
+    } else {
+        c_feat.resize(total);
+        c_thr.resize(total);
+    }
+    std::vector<int32_t> hidx_t;
+    std::vector<float> hw_t;
+    for (int t = 0; t < ntrees; t++) {
+        const int64_t src = (int64_t)t * cap, dst = node_off[t];
+        const int nn = n_nodes[t];
+        std::memcpy(&c_left[dst], &left[src], nn * 4);
+        std::memcpy(&c_right[dst], &right[src], nn * 4);
+        std::memcpy(&c_ninst[dst], &ninst[src], nn * 8);
+        if (!ext) {
+            std::memcpy(&c_feat[dst], &feature[src], nn * 4);
+            std::memcpy(&c_thr[dst], &thr[src], nn * 8);
+        } else {
+            std::memcpy(&c_off[dst], &off[src], nn * 8);
+            const int ni = n_int[t];
+            hidx_t.resize((size_t)ni * k);
+            hw_t.resize((size_t)ni * k);
+            if (ni > 0) {
+                IFB_CUDA(cudaMemcpy(hidx_t.data(), p.hp_idx + (int64_t)t * cap_internal * k, (size_t)ni * k * 4,
+                                    cudaMemcpyDeviceToHost));
+                IFB_CUDA(cudaMemcpy(hw_t.data(), p.hp_w + (int64_t)t * cap_internal * k, (size_t)ni * k * 4,
+                                    cudaMemcpyDeviceToHost));
+            }
+            for (int i = 0; i < nn; i++) {
+                const int s = slot[src + i];
+                if (left[src + i] != -1) {
+                    hp_idx.insert(hp_idx.end(), hidx_t.begin() + (size_t)s * k, hidx_t.begin() + (size_t)(s + 1) * k);
+                    hp_w.insert(hp_w.end(), hw_t.begin() + (size_t)s * k, hw_t.begin() + (size_t)(s + 1) * k);
+                }
+                hp_off[dst + i + 1] = (int64_t)hp_idx.size();
+            }
+        }
+    }
+    if (ext)
+        return ifb_forest_create_extended(device, ntrees, node_off.data(), c_left.data(), c_right.data(), c_ninst.data(),
+                                          c_off.data(), hp_off.data(), hp_idx.data(), hp_w.data(), n, d, out);
+    return ifb_forest_create_standard(device, ntrees, node_off.data(), c_left.data(), c_right.data(), c_feat.data(),
+                                      c_thr.data(), c_ninst.data(), n, d, out);
+}
+
+extern "C" int ifb_fit_host(int32_t device, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
+                            const ifb_fit_params *prm, ifb_forest **out) {
+    IFB_REQUIRE(out && X && prm, "null argument");
+    IFB_REQUIRE(d >= 1 && n_rows >= 1, "empty training matrix");
+    IFB_REQUIRE(layout == IFB_COL_MAJOR ? ld >= n_rows : ld >= d, "leading dimension %lld too small", (long long)ld);
+    DeviceGuard dg(device);
+    // The builder touches only numEstimators * numSamples rows, but which ones is decided on the device, so
+    // the matrix is staged whole (it is needed on the device for the threshold pass of fit anyway).
+    const size_t elems = (size_t)(layout == IFB_COL_MAJOR ? (int64_t)d * ld : n_rows * ld);
+    float *dX = nullptr;
+    IFB_CUDA(cudaMalloc((void **)&dX, elems * 4));
+    cudaError_t e = cudaMemcpy(dX, X, elems * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(dX);
+        set_error("host->device copy failed: %s", cudaGetErrorString(e));
+        return IFB_ECUDA;
+    }
+    int rc = ifb_fit_device(device, dX, n_rows, d, ld, layout, prm, out, nullptr);
+    cudaFree(dX);
+    return rc;
 }

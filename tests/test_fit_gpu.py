@@ -1,0 +1,114 @@
+"""GPU parity tests of the fit hot path: the CUDA tree builder vs the oracle's restatement of
+IsolationTree.fit / ExtendedIsolationTree.fit (bit-identical node tables for identical seeds), plus the
+reference's own statistical acceptance bands."""
+import numpy as np
+import pytest
+
+from conftest import synth_mixture
+from test_oracle_golden import _auroc
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def fit_gpu(nat, X, T, n, num_features=None, bootstrap=False, seed=1, parts=1, ext=-1, tree_range=(0, 0), colmajor=True):
+    d = X.shape[1]
+    prm = nat.FitParams(T, n, num_features or d, int(bootstrap), seed, parts, ext, tree_range[0], tree_range[1])
+    Xd = torch.from_numpy(np.ascontiguousarray(X.T)).cuda().t() if colmajor else torch.from_numpy(X).cuda()
+    return nat.fit_device(Xd, prm)
+
+
+def assert_tables_equal(got, ref):
+    keys = ["node_off", "left", "right", "num_instances"]
+    keys += ["offset", "hp_off", "hp_idx", "hp_w"] if ref["extended"] else ["feature", "threshold"]
+    for k in keys:
+        assert np.array_equal(got[k], ref[k]), f"{k} differs"
+
+
+@pytest.mark.parametrize("n_rows,d,T,n,nf,boot,seed,parts", [
+    (5000, 10, 100, 256, None, False, 1, 1),
+    (20000, 32, 64, 256, None, False, 7, 4),
+    (3000, 9, 20, 100, 4, False, 3, 1),        # maxFeatures < 1, non power-of-two samples
+    (600, 5, 30, 256, None, True, 5, 2),       # bootstrap
+    (40000, 128, 16, 256, 64, False, 11, 1),
+    (2000, 3, 8, 1000, None, False, 2, 1),     # more samples than threads
+    (300, 4, 5, 2, None, False, 9, 1),         # smallest legal sample
+])
+def test_standard_fit_bit_identical(nat, oracle, n_rows, d, T, n, nf, boot, seed, parts):
+    X = synth_mixture(n_rows, d, 100 + d)
+    X[::5, 0] = 1.0                             # repeated values: exercises the constant-feature retry
+    ref = oracle.fit_forest(X, T, n, num_features=nf, bootstrap=boot, random_seed=seed, num_partitions=parts)
+    got = fit_gpu(nat, X, T, n, nf, boot, seed, parts).export()
+    assert_tables_equal(got, ref)
+    got_rm = fit_gpu(nat, X, T, n, nf, boot, seed, parts, colmajor=False).export()
+    assert_tables_equal(got_rm, ref)
+
+
+@pytest.mark.parametrize("n_rows,d,T,n,nf,ext,seed", [
+    (5000, 6, 50, 256, None, 5, 1),
+    (5000, 6, 50, 256, None, 0, 1),
+    (8000, 64, 24, 256, None, 63, 3),
+    (3000, 12, 10, 128, 7, 3, 4),
+    (1000, 200, 4, 64, None, 199, 5),
+])
+def test_extended_fit_bit_identical(nat, oracle, n_rows, d, T, n, nf, ext, seed):
+    X = synth_mixture(n_rows, d, 300 + d)
+    ref = oracle.fit_forest(X, T, n, num_features=nf, random_seed=seed, ext_level=ext)
+    got = fit_gpu(nat, X, T, n, nf, seed=seed, ext=ext).export()
+    assert_tables_equal(got, ref)
+
+
+def test_identical_rows_and_constant_features(nat, oracle):
+    same = np.ones((64, 3), np.float32)
+    got = fit_gpu(nat, same, 5, 16, seed=3).export()
+    assert (np.diff(got["node_off"]) == 1).all() and (got["num_instances"] == 16).all()
+    assert_tables_equal(got, oracle.fit_forest(same, 5, 16, random_seed=3))
+    # extended IF does NOT retry: degenerate splits create size-0 leaves (README remark)
+    X = synth_mixture(2000, 4, 8)
+    X[:, 1] = 2.5
+    ref = oracle.fit_forest(X, 20, 256, random_seed=6, ext_level=0)
+    got = fit_gpu(nat, X, 20, 256, seed=6, ext=0).export()
+    assert_tables_equal(got, ref)
+    assert (got["num_instances"] == 0).any()
+
+
+def test_tree_shards_are_independent_of_the_split(nat, oracle):
+    X = synth_mixture(10000, 16, 77)
+    whole = fit_gpu(nat, X, 24, 256, seed=13).export()
+    a = fit_gpu(nat, X, 24, 256, seed=13, tree_range=(0, 10)).export()
+    b = fit_gpu(nat, X, 24, 256, seed=13, tree_range=(10, 24)).export()
+    na = a["node_off"][-1]
+    for k in ("left", "right", "feature", "threshold", "num_instances"):
+        assert np.array_equal(np.concatenate([a[k], b[k]]), whole[k])
+    assert np.array_equal(np.concatenate([a["node_off"], b["node_off"][1:] + na]), whole["node_off"])
+
+
+def test_reference_statistical_bands(nat, oracle, golden):
+    """IFT/IsolationForestTest.scala:78-85,211-236; IFT/extended/ExtendedIsolationForestTest.scala:46-53,364-370:
+    the acceptance bands the reference's own fit must meet, applied to GPU fit + GPU scoring."""
+    Xm, ym = golden.mammography["X"], golden.mammography["label"]
+    Xs, ys = golden.shuttle["X"], golden.shuttle["label"]
+
+    def run(X, ext):
+        F = fit_gpu(nat, X, 100, 256, seed=1, ext=ext)
+        return F.score_device(torch.from_numpy(np.ascontiguousarray(X.T)).cuda().t()).cpu().numpy()
+
+    assert abs(_auroc(run(Xm, -1), ym) - 0.86) < 0.02
+    s = run(Xs, -1)
+    assert _auroc(s, ys) > 0.99
+    assert abs(s[ys == 1].mean() - 0.61) < 0.02 and abs(s[ys == 0].mean() - 0.41) < 0.02
+    assert abs(_auroc(run(Xm, 5), ym) - 0.86) < 0.025
+    assert abs(_auroc(run(Xm, 0), ym) - 0.86) < 0.025
+    assert _auroc(run(Xs, 8), ys) > 0.99
+
+
+def test_fit_argument_errors(nat):
+    X = torch.zeros(100, 4, device="cuda")
+    with pytest.raises(ValueError, match="but >=2 samples are required"):
+        nat.fit_device(X, nat.FitParams(10, 1, 4, 0, 1, 1, -1, 0, 0))
+    with pytest.raises(ValueError, match="but only 100 samples are in the input dataset"):
+        nat.fit_device(X, nat.FitParams(10, 101, 4, 0, 1, 1, -1, 0, 0))
+    with pytest.raises(ValueError, match="but only 4 features are available"):
+        nat.fit_device(X, nat.FitParams(10, 50, 5, 0, 1, 1, -1, 0, 0))
+    with pytest.raises(ValueError, match=r"extensionLevel given invalid value 4, but must be in \[0, 3\]"):
+        nat.fit_device(X, nat.FitParams(10, 50, 4, 0, 1, 1, 4, 0, 0))
