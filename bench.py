@@ -139,11 +139,13 @@ def run_reference(args, wl_name, wl):
     train = mixture_numpy(min(TRAIN_ROWS, 1 << 18), d, 4242)
     tables = O.fit_forest(train, T, ns, random_seed=1, ext_level=ext)
     forest = O.Forest(tables)
-    # bounded sample per step: ~4 s of CPU work, never more than the workload
+    # bounded sample per step: the whole --steps/--warmup run is sized to about 75 s of CPU work
     probe_rows = min(n, 100_000)
     Xp = mixture_numpy(probe_rows, d, 1002)
+    forest.score(Xp, threads=cores)
     t0 = time.perf_counter(); forest.score(Xp, threads=cores); rate = probe_rows / (time.perf_counter() - t0)
-    rows = int(min(n, max(probe_rows, rate * 4.0)))
+    per_step_s = min(4.0, 75.0 / max(1, args.steps + args.warmup))
+    rows = int(min(n, max(20_000, rate * per_step_s)))
     X = mixture_numpy(rows, d, 1002)
     for _ in range(args.warmup):
         forest.score(X, threads=cores)

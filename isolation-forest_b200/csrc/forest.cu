@@ -225,7 +225,7 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
             *out = p;
             return IFB_OK;
         }
-    IFB_REQUIRE(d >= 1 && d <= 4094, "standard scoring supports 1 <= d <= 4094 features, got %d", d);
+    IFB_REQUIRE(d >= 1 && d <= 16382, "standard scoring supports 1 <= d <= 16382 features, got %d", d);
     IFB_REQUIRE(f->max_feature_index < d, "forest reads feature index %d but the matrix has only %d columns",
                 f->max_feature_index, d);
     const int smem_max = device_smem_optin(f->device);
@@ -278,14 +278,14 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
         int64_t trees = 0;
         while (t < T) {
             int64_t n = f->bfs_off[t + 1] - f->bfs_off[t];
-            if ((words + n) * 8 + (trees + 1) * 4 > room && trees > 0) break;
+            if (((words + n) * 8 + (trees + 1) * 4 > room || trees >= std_top_table_max_trees()) && trees > 0) break;
             words += n;
             trees++;
             t++;
         }
         c.tree_end = t;
         c.node_count = (int32_t)words;
-        IFB_REQUIRE(words * 4 < (1 << 20), "chunk too large for 20-bit child offsets");
+        IFB_REQUIRE(words < (1 << 16), "chunk too large for 16-bit child indices");
         val.push_back(0.f);
         meta.push_back(0u);
         int64_t w = 1;
@@ -297,14 +297,22 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
                 const int64_t self = w + q;
                 val.push_back(f->h_val[g]);
                 if (f->h_child[g] < 0) {
-                    meta.push_back(((uint32_t)d << 20) | (uint32_t)((self - 1) * 4));
+                    meta.push_back(((uint32_t)(self - 1) << 16) | (uint32_t)d);
                 } else {
-                    meta.push_back((f->h_meta_feat[g] << 20) | (uint32_t)((w + f->h_child[g]) * 4));
+                    meta.push_back(((uint32_t)(w + f->h_child[g]) << 16) | f->h_meta_feat[g]);
                 }
             }
             w += n;
         }
         p->chunks.push_back(c);
+    }
+    // kernel-parameter tables (tree levels 0 and 1) per chunk
+    p->h_top.assign(p->chunks.size() * std_top_table_bytes(), 0);
+    for (size_t ci = 0; ci < p->chunks.size(); ci++) {
+        const StdChunk &c = p->chunks[ci];
+        std_fill_top_table(p->h_top.data() + ci * std_top_table_bytes(), val.data() + c.node_begin,
+                           meta.data() + c.node_begin, roots.data() + c.tree_begin, c.tree_end - c.tree_begin,
+                           R < 256 ? R : 256);
     }
     p->total_words = (int64_t)val.size();
     DeviceGuard dg(f->device);

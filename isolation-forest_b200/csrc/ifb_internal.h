@@ -58,10 +58,11 @@ struct DeviceGuard {
 // whose lanes sit on different nodes of one level touches distinct banks for the top levels:
 //     val [g] : internal: smallest f32 >= splitValue  (x < splitValue  <=>  x < val, x being f32)
 //               leaf    : (float)depth + avgPathLength(numInstances)   (the value pathLength returns)
-//     meta[g] : (feature << 20) | child_off   where child_off (20 bits) = BYTE offset of the LEFT child in
-//               the chunk-local val[] array; leaves store feature = d (the pseudo column of NaNs every
-//               row tile carries) and child_off = self - 4, so "next = child_off + 4*!(x < val)" maps a
-//               leaf onto itself: walks run a fixed number of steps with no per-level branch.
+//     meta[g] : (child << 16) | feature   where child = WORD index of the LEFT child in the chunk-local
+//               val[] array; leaves store feature = d (the pseudo column of NaNs every row tile carries)
+//               and child = self - 1, so "next = child + !(x < val)" maps a leaf onto itself: walks run
+//               a fixed number of steps with no per-level branch.  Levels 0 and 1 of every tree are also
+//               flattened into a kernel-parameter table (constant bank, warp-uniform loads).
 // Trees are grouped into chunks whose tables fit in shared memory next to the row tiles.
 // ------------------------------------------------------------------------------------------------
 struct StdChunk {
@@ -112,6 +113,7 @@ struct ifb_forest {
         uint32_t *d_meta = nullptr;
         uint32_t *d_tree_root = nullptr;  // [T] chunk-local word index of each tree's root
         int64_t total_words = 0;
+        std::vector<unsigned char> h_top;  // per chunk: the TopTable kernel parameter (tree levels 0 and 1)
     };
     std::mutex plan_mu;
     std::vector<StdPlan *> std_plans;
@@ -142,6 +144,10 @@ int build_extended_tables(ifb_forest *f);
 int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out);
 
 // score_std.cu
+size_t std_top_table_bytes();
+int std_top_table_max_trees();
+void std_fill_top_table(void *dst, const float *val, const uint32_t *meta, const uint32_t *root_byte, int n_trees,
+                        int rows_per_box);
 int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const float *X, int64_t n_rows,
                           int32_t d, int64_t ld, int32_t layout, double *scores, int32_t *depth_sum,
                           float *path_sum, bool accumulate_only, cudaStream_t stream);

@@ -18,7 +18,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "ifb_internal.h"
 
@@ -27,6 +29,22 @@ namespace ifb {
 namespace {
 
 constexpr int kStages = 2;
+constexpr int kMaxTopTrees = 256;   // trees per chunk whose two top levels ride in the kernel parameters
+
+// Levels 0 and 1 of every tree of the chunk, passed as a kernel parameter (constant bank): all 32 lanes of a
+// warp walk the same tree, so these loads are warp-uniform and cost no shared-memory wavefronts.
+struct TopEntry {
+    float thr0;          // root: val word
+    uint32_t f0;         // root: byte offset of its feature column inside a row sub-tile (feature * RB * 4)
+    uint32_t c0;         // root: byte offset of its left child in val[]
+    float thrL, thrR;    // the two level-1 candidates (nodes at c0 and c0 + 4)
+    uint32_t fL, fR;
+    uint32_t cL, cR;
+    uint32_t pad[3];
+};
+struct TopTable {
+    TopEntry e[kMaxTopTrees];
+};
 
 struct ScoreStdParams {
     const float *X;          // column-major matrix (fallback loader) -- also the TMA source
@@ -60,18 +78,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// Bounded wait: a TMA that never lands (bad descriptor, lost transaction) must surface as a launch failure,
+// not as a hung GPU.  ~2^31 polls of a few ns each is tens of seconds, far beyond any legitimate wait.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < 0x7fffffffu; ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int32_t c0, int32_t c1,
                                             uint64_t *bar) {
@@ -95,19 +119,39 @@ __host__ __device__ inline SmemLayout make_layout(int n_trees, int chunk_words, 
     SmemLayout L;
     L.bars = 0;
     L.roots = 64;
-    L.val = (L.roots + (uint32_t)n_trees * 4 + 15u) & ~15u;
+    L.val = 64;
     L.meta = L.val + (uint32_t)chunk_words * 4;
     L.tiles = (L.meta + (uint32_t)chunk_words * 4 + 127u) & ~127u;
     L.total = L.tiles + (uint32_t)kStages * (uint32_t)R * (uint32_t)(d + 1) * 4u;
     return L;
 }
 
-template <int R, int C, bool USE_TMA, bool WANT_DEPTH>
+// One generic level of one walk.  PTX pins the instruction mix: 3 LDS + {LOP3, SHF} on the ALU pipe +
+// {IMAD, IMAD} on the FMA pipe + FSET, so that neither math pipe becomes the limiter.
+//   meta = (left-child WORD index << 16) | feature;   next = child*4 + 4*!(x < val)
+__device__ __forceinline__ uint32_t walk_step(uint32_t node, uint32_t val_s, uint32_t meta_s, uint32_t xrow_s,
+                                              uint32_t col_bytes, uint32_t d, int32_t &depth, bool want_depth) {
+    float v, x;
+    uint32_t m, feat, xaddr, cb, ge, next;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(val_s + node));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(meta_s + node));
+    asm("and.b32 %0, %1, 0xFFFF;" : "=r"(feat) : "r"(m));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(xaddr) : "r"(feat), "r"(col_bytes), "r"(xrow_s));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xaddr));
+    asm("shr.u32 %0, %1, 14;" : "=r"(cb) : "r"(m));            // (child << 2) | (feat >> 14) == child*4
+    asm("set.geu.u32.f32 %0, %1, %2;" : "=r"(ge) : "f"(x), "f"(v));   // 0xFFFFFFFF when !(x < v) (incl. NaN)
+    asm("mad.lo.s32 %0, %1, -4, %2;" : "=r"(next) : "r"(ge), "r"(cb));
+    if (want_depth) depth += (feat != d) ? 1 : 0;
+    return next;
+}
+
+template <int R, int C, bool USE_TMA, bool WANT_DEPTH, int DEEP>
 __global__ void __launch_bounds__(R, 1)
 score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_rem,
-                 const ScoreStdParams p) {
+                 const __grid_constant__ TopTable top, const ScoreStdParams p) {
     constexpr int RB = R < 256 ? R : 256;  // rows per TMA box == row stride of the smem tile
     constexpr int NSUB = R / RB;
+    constexpr uint32_t COL_BYTES = RB * 4;
     extern __shared__ __align__(1024) unsigned char smem[];
     const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, p.d);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
@@ -122,9 +166,6 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
-        uint32_t *sroots = reinterpret_cast<uint32_t *>(smem + L.roots);
-        for (int i = tid; i < p.n_trees; i += R) sroots[i] = p.roots[i];
-        // val and meta are 16-byte aligned in both spaces (chunk starts are padded on the host)
         float *sval = reinterpret_cast<float *>(smem + L.val);
         uint32_t *smeta = reinterpret_cast<uint32_t *>(smem + L.meta);
         for (int i = tid; i < p.chunk_words; i += R) {
@@ -181,12 +222,13 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
         }
     }
 
-    const unsigned char *sbase = smem;
-    const uint32_t val_off = L.val, meta_off = L.meta;
-    const uint32_t *sroots = reinterpret_cast<const uint32_t *>(smem + L.roots);
+    const uint32_t val_s = smem_u32(smem + L.val), meta_s = smem_u32(smem + L.meta);
+    const uint32_t tiles_s = smem_u32(smem + L.tiles);
     const int sub = tid / RB, rl = tid % RB;
     const int n_trees = p.n_trees;
-    const int max_depth = p.max_depth;
+    // levels 0 and 1 come from `top`; DEEP >= 0 fixes the remaining level count at compile time (full unroll)
+    const int deep_levels = DEEP >= 0 ? DEEP : (p.max_depth > 2 ? p.max_depth - 2 : 0);
+    const uint32_t leaf_col = (uint32_t)d * COL_BYTES;
 
     for (int64_t k = 0; tile < p.n_tiles; tile += stride, ++k) {
         const int stage = (int)(k & 1);
@@ -196,8 +238,7 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
             load_tile_plain(tile, stage);
             __syncthreads();
         }
-        const unsigned char *xrow = smem + L.tiles +
-                                    ((uint32_t)stage * tile_floats + (uint32_t)sub * sub_floats + (uint32_t)rl) * 4u;
+        const uint32_t xrow_s = tiles_s + ((uint32_t)stage * tile_floats + (uint32_t)sub * sub_floats + (uint32_t)rl) * 4u;
         const int64_t row = tile * R + tid;
         const bool live = row < p.n_rows;
 
@@ -208,39 +249,54 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
             if (WANT_DEPTH) dsum = p.depth_sum[row];
         }
 
-        int t = 0;
-        for (; t + C <= n_trees; t += C) {
-            uint32_t node[C];
+        // levels 0 and 1 from the constant bank, then `deep_levels` generic steps, C trees in flight
+        auto top_levels = [&](int t) -> uint32_t {
+            const TopEntry &e = top.e[t];
+            float x0, x1;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(xrow_s + e.f0));
+            const bool lt0 = x0 < e.thr0;
+            const float thr1 = lt0 ? e.thrL : e.thrR;
+            const uint32_t f1 = lt0 ? e.fL : e.fR;
+            const uint32_t c1 = lt0 ? e.cL : e.cR;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x1) : "r"(xrow_s + f1));
+            if (WANT_DEPTH) dsum += (e.f0 != leaf_col ? 1 : 0) + (f1 != leaf_col ? 1 : 0);
+            return c1 + ((x1 < thr1) ? 0u : 4u);
+        };
+
+        // walk CC trees at once (independent dependency chains), add their path lengths in tree order
+        auto walk_group = [&](int t0, auto cc_tag) {
+            constexpr int CC = decltype(cc_tag)::value;
+            uint32_t node[CC];
 #pragma unroll
-            for (int c = 0; c < C; c++) node[c] = sroots[t + c];
+            for (int c = 0; c < CC; c++) node[c] = top_levels(t0 + c);
+            if constexpr (DEEP >= 0) {
+#pragma unroll
+                for (int lvl = 0; lvl < DEEP; lvl++) {
+#pragma unroll
+                    for (int c = 0; c < CC; c++)
+                        node[c] = walk_step(node[c], val_s, meta_s, xrow_s, COL_BYTES, (uint32_t)d, dsum, WANT_DEPTH);
+                }
+            } else {
 #pragma unroll 1
-            for (int lvl = 0; lvl < max_depth; lvl++) {
+                for (int lvl = 0; lvl < deep_levels; lvl++) {
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const float v = *reinterpret_cast<const float *>(sbase + val_off + node[c]);
-                    const uint32_t m = *reinterpret_cast<const uint32_t *>(sbase + meta_off + node[c]);
-                    const uint32_t feat = m >> 20;
-                    const float x = *reinterpret_cast<const float *>(xrow + feat * (uint32_t)(RB * 4));
-                    if (WANT_DEPTH) dsum += (feat != (uint32_t)d) ? 1 : 0;
-                    node[c] = (m & 0xFFFFFu) + ((x < v) ? 0u : 4u);
+                    for (int c = 0; c < CC; c++)
+                        node[c] = walk_step(node[c], val_s, meta_s, xrow_s, COL_BYTES, (uint32_t)d, dsum, WANT_DEPTH);
                 }
             }
 #pragma unroll
-            for (int c = 0; c < C; c++) s = s + *reinterpret_cast<const float *>(sbase + val_off + node[c]);
-        }
-        for (; t < n_trees; t++) {
-            uint32_t node = sroots[t];
-#pragma unroll 1
-            for (int lvl = 0; lvl < max_depth; lvl++) {
-                const float v = *reinterpret_cast<const float *>(sbase + val_off + node);
-                const uint32_t m = *reinterpret_cast<const uint32_t *>(sbase + meta_off + node);
-                const uint32_t feat = m >> 20;
-                const float x = *reinterpret_cast<const float *>(xrow + feat * (uint32_t)(RB * 4));
-                if (WANT_DEPTH) dsum += (feat != (uint32_t)d) ? 1 : 0;
-                node = (m & 0xFFFFFu) + ((x < v) ? 0u : 4u);
+            for (int c = 0; c < CC; c++) {
+                float lv;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lv) : "r"(val_s + node[c]));
+                s = s + lv;
             }
-            s = s + *reinterpret_cast<const float *>(sbase + val_off + node);
-        }
+        };
+        int t = 0;
+        for (; t + C <= n_trees; t += C) walk_group(t, std::integral_constant<int, C>{});
+        if constexpr (C >= 16) if (t + 8 <= n_trees) { walk_group(t, std::integral_constant<int, 8>{}); t += 8; }
+        if constexpr (C >= 8) if (t + 4 <= n_trees) { walk_group(t, std::integral_constant<int, 4>{}); t += 4; }
+        if constexpr (C >= 4) if (t + 2 <= n_trees) { walk_group(t, std::integral_constant<int, 2>{}); t += 2; }
+        for (; t < n_trees; t++) walk_group(t, std::integral_constant<int, 1>{});
 
         if (live) {
             if (p.finalize) {
@@ -299,21 +355,48 @@ int make_tmap(CUtensorMap *map, const float *X, int64_t n_rows, int32_t d, int64
 }
 
 template <int R, int C>
-int launch_variant(bool use_tma, bool want_depth, const CUtensorMap &m0, const CUtensorMap &m1,
+int launch_variant(bool use_tma, bool want_depth, const CUtensorMap &m0, const CUtensorMap &m1, const TopTable &top,
                    const ScoreStdParams &p, int grid, size_t smem, cudaStream_t stream) {
     auto go = [&](auto kern) -> int {
         IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, R, smem, stream>>>(m0, m1, p);
+        kern<<<grid, R, smem, stream>>>(m0, m1, top, p);
         IFB_CUDA(cudaGetLastError());
         count_launch();
         return IFB_OK;
     };
+    const bool deep6 = p.max_depth == 8 && !want_depth && use_tma;
+    if (deep6) return go(score_std_kernel<R, C, true, false, 6>);
     if (use_tma)
-        return want_depth ? go(score_std_kernel<R, C, true, true>) : go(score_std_kernel<R, C, true, false>);
-    return want_depth ? go(score_std_kernel<R, C, false, true>) : go(score_std_kernel<R, C, false, false>);
+        return want_depth ? go(score_std_kernel<R, C, true, true, -1>) : go(score_std_kernel<R, C, true, false, -1>);
+    return want_depth ? go(score_std_kernel<R, C, false, true, -1>) : go(score_std_kernel<R, C, false, false, -1>);
 }
 
 }  // namespace
+
+size_t std_top_table_bytes() { return sizeof(TopTable); }
+int std_top_table_max_trees() { return kMaxTopTrees; }
+
+// Fill the kernel-parameter table of one chunk from its val/meta words (host side, called by the planner).
+void std_fill_top_table(void *dst, const float *val, const uint32_t *meta, const uint32_t *root_byte, int n_trees,
+                        int rows_per_box) {
+    TopTable *tt = reinterpret_cast<TopTable *>(dst);
+    std::memset(tt, 0, sizeof(TopTable));
+    const uint32_t col = (uint32_t)rows_per_box * 4u;
+    for (int t = 0; t < n_trees; t++) {
+        TopEntry &e = tt->e[t];
+        const uint32_t r = root_byte[t] / 4;
+        e.thr0 = val[r];
+        e.f0 = (meta[r] & 0xFFFFu) * col;
+        e.c0 = (meta[r] >> 16) * 4u;
+        const uint32_t l = e.c0 / 4, rr = l + 1;
+        e.thrL = val[l];
+        e.thrR = val[rr];
+        e.fL = (meta[l] & 0xFFFFu) * col;
+        e.fR = (meta[rr] & 0xFFFFu) * col;
+        e.cL = (meta[l] >> 16) * 4u;
+        e.cR = (meta[rr] >> 16) * 4u;
+    }
+}
 
 int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const float *X, int64_t n_rows, int32_t d,
                           int64_t ld, int32_t layout, double *scores, int32_t *depth_sum, float *path_sum,
@@ -359,7 +442,7 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
         p.rem_d = rem_d;
         p.val = plan->d_val + c.node_begin;
         p.meta = plan->d_meta + c.node_begin;
-        p.roots = plan->d_tree_root + c.tree_begin;
+        p.roots = nullptr;
         p.chunk_words = c.node_count;
         p.n_trees = c.tree_end - c.tree_begin;
         p.max_depth = f->max_depth;
@@ -372,13 +455,14 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
         p.depth_sum = depth_sum;
         p.n_tiles = n_tiles;
         const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, d);
+        const TopTable &top = *reinterpret_cast<const TopTable *>(plan->h_top.data() + (size_t)ci * sizeof(TopTable));
         int rc;
         switch (R) {
-            case 512: rc = launch_variant<512, 2>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
-            case 256: rc = launch_variant<256, 4>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
-            case 128: rc = launch_variant<128, 8>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
-            case 64: rc = launch_variant<64, 8>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
-            default: rc = launch_variant<32, 8>(use_tma, want_depth, m0, m1, p, grid, L.total, stream); break;
+            case 512: rc = launch_variant<512, 4>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
+            case 256: rc = launch_variant<256, 8>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
+            case 128: rc = launch_variant<128, 16>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
+            case 64: rc = launch_variant<64, 16>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
+            default: rc = launch_variant<32, 16>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
         }
         if (rc) return rc;
     }
