@@ -66,6 +66,9 @@ IFB_API int ifb_host_alloc(size_t bytes, void **ptr);
 IFB_API int ifb_host_free(void *ptr);
 IFB_API int ifb_device_alloc(int32_t device, size_t bytes, void **ptr);
 IFB_API int ifb_device_free(int32_t device, void *ptr);
+/* Blocking copies between host memory and device memory obtained from ifb_device_alloc. */
+IFB_API int ifb_copy_to_device(int32_t device, void *dst_device, const void *src_host, size_t bytes);
+IFB_API int ifb_copy_to_host(int32_t device, void *dst_host, const void *src_device, size_t bytes);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* forest handles                                                                                  */

@@ -8,5 +8,8 @@ built into ``libifb200.so``), ``_native.py`` (ctypes binding) and the host-side 
 Estimator / Model interface.
 """
 from . import _native  # noqa: F401
+from .estimators import (ExtendedIsolationForest, ExtendedIsolationForestModel, IllegalArgumentException,  # noqa: F401
+                         IllegalStateException, IsolationForest, IsolationForestModel, Scored)
 
-__all__ = ["_native"]
+__all__ = ["_native", "IsolationForest", "IsolationForestModel", "ExtendedIsolationForest",
+           "ExtendedIsolationForestModel", "IllegalArgumentException", "IllegalStateException", "Scored"]

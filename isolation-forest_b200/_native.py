@@ -50,6 +50,8 @@ SYMBOLS = {
     "ifb_host_free": (C.c_int, [C.c_void_p]),
     "ifb_device_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]),
     "ifb_device_free": (C.c_int, [C.c_int32, C.c_void_p]),
+    "ifb_copy_to_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ifb_copy_to_host": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ifb_forest_create_standard": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 6 + [C.c_int32, C.c_int32,
                                                                                        C.POINTER(C.c_void_p)]),
     "ifb_forest_create_extended": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_int32, C.c_int32,

@@ -394,6 +394,19 @@ int ifb_device_free(int32_t device, void *ptr) {
     return IFB_OK;
 }
 
+int ifb_copy_to_device(int32_t device, void *dst, const void *src, size_t bytes) {
+    IFB_REQUIRE(bytes == 0 || (dst && src), "null buffer");
+    DeviceGuard dg(device);
+    IFB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return IFB_OK;
+}
+int ifb_copy_to_host(int32_t device, void *dst, const void *src, size_t bytes) {
+    IFB_REQUIRE(bytes == 0 || (dst && src), "null buffer");
+    DeviceGuard dg(device);
+    IFB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return IFB_OK;
+}
+
 static int check_device(int32_t device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
