@@ -211,6 +211,54 @@ int build_extended_tables(ifb_forest *f) {
     if ((rc = up((void **)&f->d_ext_hp, hp.data(), hp.size() * 4))) return rc;
     if ((rc = up((void **)&f->d_ext_len, len.data(), len.size() * 4))) return rc;
     if ((rc = up((void **)&f->d_ext_tree_node, tree_node.data(), tree_node.size() * 8))) return rc;
+
+    // ---- per-tree blobs for the dense kernel ----
+    if (f->ext_dense_identity && k <= 64) {
+        const int D = k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64;
+        const int WS = D + 4;  // row stride in floats: 16-byte units odd => per-lane LDS.128 gathers spread over banks
+        std::vector<unsigned char> blob;
+        std::vector<int64_t> boff(T + 1, 0);
+        int64_t mx = 0;
+        for (int t = 0; t < T; t++) {
+            const int64_t base = f->node_off[t];
+            const int n = f->node_off[t + 1] - f->node_off[t];
+            int ni = 0;
+            for (int q = 0; q < n; q++) ni += (child[base + q] >= 0);
+            const int npad = (n + 3) & ~3, ipad = (ni + 1) & ~1;
+            const size_t bytes = 16 + (size_t)npad * 12 + (size_t)ipad * 8 + (size_t)ni * WS * 4;
+            const size_t bpad = (bytes + 15) & ~(size_t)15;
+            const size_t at = blob.size();
+            blob.resize(at + bpad, 0);
+            unsigned char *B = blob.data() + at;
+            int32_t *hdr = (int32_t *)B;
+            hdr[0] = n; hdr[1] = ni; hdr[2] = npad; hdr[3] = ipad;
+            int32_t *bchild = (int32_t *)(B + 16), *bslot = bchild + npad;
+            float *bleaf = (float *)(bslot + npad);
+            double *boffs = (double *)(bleaf + npad);
+            float *bw = (float *)(boffs + ipad);
+            int sl = 0;
+            for (int q = 0; q < n; q++) {
+                const int64_t g = base + q;
+                bchild[q] = child[g];
+                bleaf[q] = leaf[g];
+                if (child[g] >= 0) {
+                    bslot[q] = sl;
+                    boffs[sl] = off[g];
+                    const int64_t src = (int64_t)hp[g] * k;
+                    for (int i = 0; i < k; i++) bw[(size_t)sl * WS + i] = w[src + i];
+                    sl++;
+                } else {
+                    bslot[q] = -1;
+                }
+            }
+            boff[t + 1] = (int64_t)blob.size();
+            mx = std::max<int64_t>(mx, (int64_t)bpad);
+        }
+        f->ext_blob_D = D;
+        f->ext_blob_max = mx;
+        if ((rc = up((void **)&f->d_ext_blob, blob.data(), blob.size()))) return rc;
+        if ((rc = up((void **)&f->d_ext_blob_off, boff.data(), boff.size() * 8))) return rc;
+    }
     return IFB_OK;
 }
 
@@ -346,6 +394,8 @@ ifb_forest::~ifb_forest() {
     cudaFree(d_ext_hp);
     cudaFree(d_ext_len);
     cudaFree(d_ext_tree_node);
+    cudaFree(d_ext_blob);
+    cudaFree(d_ext_blob_off);
 }
 
 using namespace ifb;

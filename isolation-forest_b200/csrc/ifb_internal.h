@@ -130,6 +130,12 @@ struct ifb_forest {
     int64_t *d_ext_tree_node = nullptr;  // [T+1]
     bool ext_dense_identity = false;
     int64_t ext_internal_slots = 0;
+    // fully-extended forests with k <= 64: one self-contained blob per tree (header, child[], slot[], leaf[],
+    // off[], w[internal][D+4]) that score_ext_dense_kernel streams into shared memory with a bulk async copy
+    unsigned char *d_ext_blob = nullptr;
+    int64_t *d_ext_blob_off = nullptr;   // [T+1] byte offsets (16-byte aligned)
+    int32_t ext_blob_D = 0;              // padded hyperplane width (8/16/32/64), 0 = no blob layout
+    int64_t ext_blob_max = 0;            // largest blob in bytes
 
     int64_t device_bytes = 0;
 

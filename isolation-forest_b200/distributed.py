@@ -1,0 +1,92 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for the collectives.
+
+Two layouts:
+  * rows sharded, forest replicated -- what the reference itself does (broadcast trees, row-parallel transform,
+    IF/IsolationForestModel.scala:129-142): no data-path collective at all;
+  * trees sharded (BASELINE.json config 4): every rank scores ALL rows against its slice of the ensemble,
+    one all-reduce(sum) of the per-row f32 path-length sums (and, optionally, the exact int32 depth sums),
+    then the 2^(-E/c) epilogue with the FULL ensemble size.  Fit under the same layout needs no collective
+    beyond gathering the finished node tables, because a tree depends only on (seed, P, tree id, data).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def tree_shard(num_trees: int, rank: int, world: int):
+    """Contiguous, balanced slice [t0, t1) of the ensemble owned by `rank`."""
+    return rank * num_trees // world, (rank + 1) * num_trees // world
+
+
+def row_shard(num_rows: int, rank: int, world: int):
+    return rank * num_rows // world, (rank + 1) * num_rows // world
+
+
+_TABLE_KEYS_STD = ("left", "right", "feature", "threshold", "num_instances")
+_TABLE_KEYS_EXT = ("left", "right", "num_instances", "offset")
+
+
+def merge_tables(shards: list) -> dict:
+    """Concatenate forest-table shards (in rank order) into one forest."""
+    first = shards[0]
+    ext = bool(first["extended"])
+    out = {k: first[k] for k in ("extended", "num_samples", "total_num_features") if k in first}
+    out["num_trees"] = int(sum(int(s["num_trees"]) for s in shards))
+    offs, base = [np.zeros(1, np.int32)], 0
+    for s in shards:
+        offs.append((np.asarray(s["node_off"][1:], np.int64) + base).astype(np.int32))
+        base += int(s["node_off"][-1])
+    out["node_off"] = np.concatenate(offs)
+    for k in (_TABLE_KEYS_EXT if ext else _TABLE_KEYS_STD):
+        out[k] = np.concatenate([np.asarray(s[k]) for s in shards])
+    if ext:
+        hoffs, hbase = [np.zeros(1, np.int64)], 0
+        for s in shards:
+            hoffs.append(np.asarray(s["hp_off"][1:], np.int64) + hbase)
+            hbase += int(s["hp_off"][-1])
+        out["hp_off"] = np.concatenate(hoffs)
+        out["hp_idx"] = np.concatenate([np.asarray(s["hp_idx"]) for s in shards])
+        out["hp_w"] = np.concatenate([np.asarray(s["hp_w"]) for s in shards])
+    return out
+
+
+def gather_tables(local_tables: dict, group=None) -> dict:
+    """all_gather of the per-rank table shards (KBs..MBs) -> the full forest on every rank."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    shards = [None] * world
+    dist.all_gather_object(shards, local_tables, group=group)
+    return merge_tables(shards)
+
+
+def fit_tree_sharded(X, fit_params, group=None):
+    """Each rank builds trees [t0, t1) of the ensemble on its own GPU; returns (local NativeForest, full tables)."""
+    import torch.distributed as dist
+
+    from . import _native as nat
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    t0, t1 = tree_shard(fit_params.num_estimators, rank, world)
+    p = nat.FitParams(fit_params.num_estimators, fit_params.num_samples, fit_params.num_features, fit_params.bootstrap,
+                      fit_params.random_seed, fit_params.num_partitions, fit_params.extension_level, t0, t1)
+    local = nat.fit_device(X, p)
+    return local, gather_tables(local.export(), group)
+
+
+def score_tree_sharded(local_forest, X, total_num_trees: int, num_samples: int, group=None, want_depth=False):
+    """Tree-sharded transform: partial sums -> all_reduce -> scores (identical on every rank)."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _native as nat
+
+    n = X.shape[0]
+    psum = torch.zeros(n, dtype=torch.float32, device=X.device)
+    dsum = torch.zeros(n, dtype=torch.int32, device=X.device) if want_depth else None
+    local_forest.score_partial_device(X, psum, dsum)
+    dist.all_reduce(psum, group=group)
+    if want_depth:
+        dist.all_reduce(dsum, group=group)
+    scores = nat.finalize_scores_device(psum, total_num_trees, num_samples)
+    return (scores, dsum, psum) if want_depth else scores

@@ -74,7 +74,8 @@ def test_standard_synthetic(nat, oracle, dev, n, d, T):
 
 
 @pytest.mark.parametrize("n,d,T,ext", [(5_000, 8, 50, 0), (5_000, 8, 50, 3), (20_000, 64, 40, 63), (2_000, 200, 8, 199),
-                                        (3_000, 40, 16, 9)])
+                                        (3_000, 40, 16, 9), (9_000, 16, 33, 15), (7_777, 32, 21, 31), (4_000, 24, 10, 23),
+                                        (300_000, 5, 12, 4), (1_000, 2, 7, 1)])
 def test_extended_synthetic(nat, oracle, dev, n, d, T, ext):
     X = synth_mixture(n, d, 2000 + d)
     tables = oracle.fit_forest(X, T, 256, random_seed=1, ext_level=ext)
@@ -82,6 +83,21 @@ def test_extended_synthetic(nat, oracle, dev, n, d, T, ext):
     ref = oracle.Forest(tables).score(X, threads=8, want_parts=True)
     assert_parity(F.score_device(colmajor_cuda(X), want_parts=True), ref)
     assert_parity(F.score_device(torch.from_numpy(X).cuda(), want_parts=True), ref)
+
+
+def test_extended_generic_and_dense_kernels_agree(nat, oracle, dev, monkeypatch):
+    """The generic kernel (any hyperplane shape) and the dense register kernel implement one contract."""
+    n, d = 50_000, 48
+    X = synth_mixture(n, d, 31)
+    tables = oracle.fit_forest(X, 25, 256, random_seed=3, ext_level=d - 1)
+    F = nat.NativeForest.from_tables(tables)
+    Xd = colmajor_cuda(X)
+    dense = [t.cpu().numpy() for t in F.score_device(Xd, want_parts=True)]
+    monkeypatch.setenv("IFB_EXT_GENERIC", "1")
+    generic = [t.cpu().numpy() for t in F.score_device(Xd, want_parts=True)]
+    for a, b in zip(dense, generic):
+        assert np.array_equal(a, b)
+    assert_parity(dense, oracle.Forest(tables).score(X, threads=8, want_parts=True))
 
 
 def test_unaligned_and_padded_layouts(nat, oracle, dev):
