@@ -210,6 +210,15 @@ int build_extended_tables(ifb_forest *f) {
     if ((rc = up((void **)&f->d_ext_child, child.data(), child.size() * 4))) return rc;
     if ((rc = up((void **)&f->d_ext_hp, hp.data(), hp.size() * 4))) return rc;
     if ((rc = up((void **)&f->d_ext_len, len.data(), len.size() * 4))) return rc;
+    {
+        std::vector<double> wabs((size_t)internal, 0.0);
+        for (int64_t sl = 0; sl < internal; sl++) {
+            double a = 0.0;
+            for (int i = 0; i < k; i++) a += std::fabs((double)w[(size_t)sl * k + i]);
+            wabs[(size_t)sl] = a;
+        }
+        if ((rc = up((void **)&f->d_ext_wabs, wabs.data(), wabs.size() * 8))) return rc;
+    }
     if ((rc = up((void **)&f->d_ext_tree_node, tree_node.data(), tree_node.size() * 8))) return rc;
 
     // ---- per-tree blobs for the dense kernel ----
@@ -256,6 +265,12 @@ int build_extended_tables(ifb_forest *f) {
         }
         f->ext_blob_D = D;
         f->ext_blob_max = mx;
+        bool wsafe = true;
+        for (float wv : w) {
+            const float a = std::fabs(wv);
+            if (!(a >= 0x1p-60f && a <= 0x1p40f)) wsafe = false;
+        }
+        f->ext_w_safe = wsafe;
         if ((rc = up((void **)&f->d_ext_blob, blob.data(), blob.size()))) return rc;
         if ((rc = up((void **)&f->d_ext_blob_off, boff.data(), boff.size() * 8))) return rc;
     }
@@ -393,6 +408,7 @@ ifb_forest::~ifb_forest() {
     cudaFree(d_ext_child);
     cudaFree(d_ext_hp);
     cudaFree(d_ext_len);
+    cudaFree(d_ext_wabs);
     cudaFree(d_ext_tree_node);
     cudaFree(d_ext_blob);
     cudaFree(d_ext_blob_off);

@@ -127,6 +127,7 @@ struct ifb_forest {
     int32_t *d_ext_child = nullptr;    // [nodes] left child (tree-local BFS) or -1 at leaves
     int32_t *d_ext_hp = nullptr;       // [nodes] hyperplane slot (index into w/idx rows) or -1 at leaves
     int32_t *d_ext_len = nullptr;      // [nodes] number of hyperplane terms (0 at leaves)
+    double *d_ext_wabs = nullptr;      // [internal_slots] sum |w_i| of the slot (rounding bound of the wide kernel)
     int64_t *d_ext_tree_node = nullptr;  // [T+1]
     bool ext_dense_identity = false;
     int64_t ext_internal_slots = 0;
@@ -136,6 +137,7 @@ struct ifb_forest {
     int64_t *d_ext_blob_off = nullptr;   // [T+1] byte offsets (16-byte aligned)
     int32_t ext_blob_D = 0;              // padded hyperplane width (8/16/32/64), 0 = no blob layout
     int64_t ext_blob_max = 0;            // largest blob in bytes
+    bool ext_w_safe = false;             // every hyperplane weight is normal with 2^-60 <= |w| <= 2^40
 
     int64_t device_bytes = 0;
 

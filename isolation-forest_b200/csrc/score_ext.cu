@@ -156,7 +156,24 @@ struct ScoreExtDenseParams {
     double *scores;
     float *path_sum;
     int32_t *depth_sum;
+    int32_t k;            // real hyperplane width (<= D)
+    int32_t w_safe;       // every weight is a normal float with 2^-60 <= |w| <= 2^40
+    uint32_t two29;       // 0x20000000, passed at run time so the multiply below stays an IMAD (FMA pipe)
+    uint64_t bias64;      // 0x38000000 << 32
 };
+
+// f32 -> f64 widening of a NORMAL, FINITE, NON-ZERO float with integer ops only (exact: rebias the exponent by
+// 1023-127 = 896, move the 23 mantissa bits to the top of the 52).  Used for a share of the hyperplane terms so
+// that the XU pipe (F2F.F64.F32, 16 lanes/clk/SM -- the measured limiter) shares the conversions with the ALU
+// and FMA pipes.  Callers guarantee the precondition (see `fast` below); everything else takes the F2F path.
+__device__ __forceinline__ double widen_int(float pf, uint32_t two29, uint64_t bias64) {
+    const uint32_t b = __float_as_uint(pf);
+    const uint32_t a = b & 0x7FFFFFFFu;
+    // one IMAD.WIDE: low word = a << 29 (mantissa tail), high word = (a >> 3) + (896 << 20)
+    const uint64_t t = (uint64_t)a * (uint64_t)two29 + bias64;
+    const uint32_t hi = (uint32_t)(t >> 32) | (b & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(uint32_t)t);
+}
 
 // One thread owns one row, held in registers (D floats, zero padded); the trees stream through a 2-slot
 // shared-memory ring, one self-contained blob per tree (forest.cu::build_extended_tables).
@@ -168,6 +185,8 @@ __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseP
     unsigned char *ring = smem_e + 128;
     const int tid = threadIdx.x;
     constexpr int WS = D + 4;
+    const uint32_t two29 = p.two29;
+    const uint64_t bias64 = p.bias64;
     if (tid == 0) {
         mbar_init_e(&bars[0], 1);
         mbar_init_e(&bars[1], 1);
@@ -193,13 +212,18 @@ __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseP
         const int64_t row = tile * R + tid;
         const bool live = row < p.n_rows;
         float xr[D];
+        bool x_safe = true;   // every real feature is finite with 2^-60 <= |x| <= 2^60 (so 2^-120 <= |w*x| <= 2^100)
 #pragma unroll
         for (int c = 0; c < D; c++) {
             float v = 0.f;
             if (live && c < p.d)
                 v = p.layout == IFB_COL_MAJOR ? __ldg(p.X + (int64_t)c * p.ld + row) : __ldg(p.X + row * p.ld + c);
             xr[c] = v;
+            const uint32_t e = (__float_as_uint(v) >> 23) & 0xFFu;
+            if (c < p.d && live) x_safe = x_safe && (e - 67u <= 120u);
         }
+        // warp-uniform: the integer widening is only used when it is exact for every lane of the warp
+        const bool fast = p.w_safe && p.k == D && __all_sync(0xffffffffu, x_safe);
         float s = (p.accumulate_only && live) ? p.path_sum[row] : 0.f;
         int32_t dsum = (p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
         for (int t = 0; t < T; t++, j++) {
@@ -220,14 +244,26 @@ __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseP
                 const int hs = slot[node];
                 const float4 *wp = reinterpret_cast<const float4 *>(w + (size_t)hs * WS);
                 double sum = 0.0;
+                if (fast) {
 #pragma unroll
-                for (int q = 0; q < D / 4; q++) {
-                    const float4 w4 = wp[q];
-                    // Float * Float -> Float (one rounding, no FMA), then += in Double, ascending index
-                    sum = __dadd_rn(sum, (double)__fmul_rn(w4.x, xr[4 * q + 0]));
-                    sum = __dadd_rn(sum, (double)__fmul_rn(w4.y, xr[4 * q + 1]));
-                    sum = __dadd_rn(sum, (double)__fmul_rn(w4.z, xr[4 * q + 2]));
-                    sum = __dadd_rn(sum, (double)__fmul_rn(w4.w, xr[4 * q + 3]));
+                    for (int q = 0; q < D / 4; q++) {
+                        const float4 w4 = wp[q];
+                        // same values, same order; terms 1 and 3 of each quad are widened on the ALU/FMA pipes
+                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.x, xr[4 * q + 0]));
+                        sum = __dadd_rn(sum, widen_int(__fmul_rn(w4.y, xr[4 * q + 1]), two29, bias64));
+                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.z, xr[4 * q + 2]));
+                        sum = __dadd_rn(sum, widen_int(__fmul_rn(w4.w, xr[4 * q + 3]), two29, bias64));
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < D / 4; q++) {
+                        const float4 w4 = wp[q];
+                        // Float * Float -> Float (one rounding, no FMA), then += in Double, ascending index
+                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.x, xr[4 * q + 0]));
+                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.y, xr[4 * q + 1]));
+                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.z, xr[4 * q + 2]));
+                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.w, xr[4 * q + 3]));
+                    }
                 }
                 node = c + ((sum < off[hs]) ? 0 : 1);
                 c = child[node];
@@ -267,6 +303,207 @@ int launch_dense(const ifb_forest *f, const ScoreExtDenseParams &p, cudaStream_t
     return IFB_OK;
 }
 
+
+// ---- wide kernel: fully extended forests with k = d > 64 (BASELINE config 5: d = 1024) -------------------
+// A warp owns G rows of the CTA's row tile (rows live in shared memory, [row][d+4] floats).  Per tree and level
+// the warp groups its rows by current node; per group it streams the node's weight row once (coalesced LDG.128)
+// and every lane accumulates, for each row of the group, the f64 sum of ITS terms (i = 128j + 4*lane + q, the
+// f32 products rounded exactly as the reference's).  The 32 partial sums are combined by a fixed shuffle tree.
+//
+// Exactness.  The reference adds the same f64 addends p_i = (double)fl32(w_i x_i) in index order; the tree above
+// is a re-association.  For ANY two summation orders of the same k addends  |S_a - S_b| <= 2 gamma_{k-1} sum|p_i|
+// (gamma_n = n u / (1 - n u), u = 2^-53), and  sum|p_i| <= max_i|x_i| * sum_i|w_i| * (1 + 2^-23) =: A.
+// Hence if |S - offset| > 4 k u A the strict comparison S < offset has the same outcome in the reference's order.
+// Otherwise (a near tie, or NaN/inf anywhere: A is then non-finite and the test fails) the visit is recomputed
+// in the reference's sequential order.  Decisions are therefore bit-exact; the fallback is taken ~never.
+struct ScoreExtWideParams {
+    const float *X;
+    int64_t n_rows, ld;
+    int32_t d, layout;
+    const float *w;
+    const double *off;
+    const double *wabs;
+    const float *leaf;
+    const int32_t *child, *hp;
+    const int64_t *tree_node;
+    int32_t num_trees, total_trees;
+    int32_t rows_per_tile;   // multiple of the warp count
+    float avg_path;
+    int32_t accumulate_only;
+    double *scores;
+    float *path_sum;
+    int32_t *depth_sum;
+};
+
+template <int G, int NW>
+__global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtWideParams p) {
+    extern __shared__ __align__(16) float xs_w[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R = G * NW;
+    const int d = p.d;
+    const int xstride = d + 4;  // floats; keeps 16-byte alignment, breaks the power-of-two row pitch
+    float *rowmax = xs_w + (size_t)R * xstride;  // [R] max |x| per row
+    const int64_t n_tiles = (p.n_rows + R - 1) / R;
+    const int chunks = d / 128;        // full 128-term chunks (4 terms per lane)
+    const int tail0 = chunks * 128;    // remaining terms [tail0, d) handled 1 per lane per step
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * R;
+        __syncthreads();
+        if (p.layout == IFB_COL_MAJOR) {
+            for (int64_t e = tid; e < (int64_t)R * d; e += NW * 32) {
+                const int c = (int)(e / R), r = (int)(e % R);
+                const int64_t row = row0 + r;
+                xs_w[(size_t)r * xstride + c] = row < p.n_rows ? __ldg(p.X + (int64_t)c * p.ld + row) : 0.f;
+            }
+        } else {
+            for (int64_t e = tid; e < (int64_t)R * d; e += NW * 32) {
+                const int r = (int)(e / d), c = (int)(e % d);
+                const int64_t row = row0 + r;
+                xs_w[(size_t)r * xstride + c] = row < p.n_rows ? __ldg(p.X + row * p.ld + c) : 0.f;
+            }
+        }
+        __syncthreads();
+        // per-row max |x| (NaN/inf propagate into the bound and force the sequential path)
+        for (int g = 0; g < G; g++) {
+            const int r = warp * G + g;
+            float m = 0.f;
+            bool bad = false;
+            for (int c = lane; c < d; c += 32) {
+                const float v = fabsf(xs_w[(size_t)r * xstride + c]);
+                bad = bad || !(v <= 3.0e38f);
+                m = fmaxf(m, v);
+            }
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            bad = __any_sync(0xffffffffu, bad);
+            if (lane == 0) rowmax[r] = bad ? __int_as_float(0x7fc00000) : m;
+        }
+        __syncwarp();
+
+        float s[G];
+        int32_t dsum[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int64_t row = row0 + warp * G + g;
+            const bool live = row < p.n_rows;
+            s[g] = (p.accumulate_only && live) ? p.path_sum[row] : 0.f;
+            dsum[g] = (p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
+        }
+        for (int t = 0; t < p.num_trees; t++) {
+            const int64_t base = p.tree_node[t];
+            int32_t node[G], ch[G];      // warp-uniform
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                node[g] = 0;
+                ch[g] = __ldg(p.child + base);
+            }
+            while (true) {
+                uint32_t pending = 0;    // rows still at an internal node
+#pragma unroll
+                for (int g = 0; g < G; g++) pending |= (ch[g] >= 0) ? (1u << g) : 0u;
+                if (!pending) break;
+                while (pending) {
+                    const int g0 = __ffs(pending) - 1;
+                    int32_t n0 = 0;
+#pragma unroll
+                    for (int g = 0; g < G; g++) if (g == g0) n0 = node[g];
+                    uint32_t grp = 0;
+#pragma unroll
+                    for (int g = 0; g < G; g++) if (((pending >> g) & 1u) && node[g] == n0) grp |= 1u << g;
+                    pending &= ~grp;
+                    const int64_t gn = base + n0;
+                    const int32_t slot = __ldg(p.hp + gn);
+                    const float *wrow = p.w + (int64_t)slot * d;
+                    double acc[G];
+#pragma unroll
+                    for (int g = 0; g < G; g++) acc[g] = 0.0;
+                    for (int j = 0; j < chunks; j++) {
+                        const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wrow + j * 128) + lane);
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            if ((grp >> g) & 1u) {
+                                const float4 x4 = *reinterpret_cast<const float4 *>(
+                                    xs_w + (size_t)(warp * G + g) * xstride + j * 128 + lane * 4);
+                                double a = acc[g];
+                                a = __dadd_rn(a, (double)__fmul_rn(w4.x, x4.x));
+                                a = __dadd_rn(a, (double)__fmul_rn(w4.y, x4.y));
+                                a = __dadd_rn(a, (double)__fmul_rn(w4.z, x4.z));
+                                a = __dadd_rn(a, (double)__fmul_rn(w4.w, x4.w));
+                                acc[g] = a;
+                            }
+                        }
+                    }
+                    for (int i = tail0 + lane; i < d; i += 32) {
+                        const float wv = __ldg(wrow + i);
+#pragma unroll
+                        for (int g = 0; g < G; g++)
+                            if ((grp >> g) & 1u)
+                                acc[g] = __dadd_rn(acc[g], (double)__fmul_rn(wv, xs_w[(size_t)(warp * G + g) * xstride + i]));
+                    }
+                    const double offv = __ldg(p.off + gn);
+                    const double wabs = __ldg(p.wabs + slot);
+                    const int32_t cbase = __ldg(p.child + gn);   // left child of n0 (same for the whole group)
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        if ((grp >> g) & 1u) {
+                            double v = acc[g];
+                            for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+                            v = __shfl_sync(0xffffffffu, v, 0);
+                            const double A = (double)rowmax[warp * G + g] * wabs * 1.0000002;
+                            const double tol = 4.0 * (double)d * 0x1.0p-53 * A;
+                            bool left;
+                            if (fabs(v - offv) > tol) {
+                                left = v < offv;
+                            } else {
+                                // near tie or non-finite data: the reference's sequential order, every lane redundantly
+                                double sq = 0.0;
+                                const float *xr = xs_w + (size_t)(warp * G + g) * xstride;
+                                for (int i = 0; i < d; i++) sq = __dadd_rn(sq, (double)__fmul_rn(__ldg(wrow + i), xr[i]));
+                                left = sq < offv;
+                            }
+                            node[g] = cbase + (left ? 0 : 1);
+                            ch[g] = __ldg(p.child + base + node[g]);
+                            dsum[g]++;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) s[g] = s[g] + __ldg(p.leaf + base + node[g]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int64_t row = row0 + warp * G + g;
+                if (row < p.n_rows) {
+                    if (!p.accumulate_only) {
+                        const float e = __fdiv_rn(s[g], (float)p.total_trees);
+                        const float z = __fdiv_rn(-e, p.avg_path);
+                        p.scores[row] = exp2((double)z);
+                    }
+                    if (p.path_sum) p.path_sum[row] = s[g];
+                    if (p.depth_sum) p.depth_sum[row] = dsum[g];
+                }
+            }
+        }
+    }
+}
+
+template <int G>
+int launch_wide(const ifb_forest *f, const ScoreExtWideParams &p0, cudaStream_t stream) {
+    constexpr int NW = 8;
+    ScoreExtWideParams p = p0;
+    p.rows_per_tile = G * NW;
+    const size_t smem = ((size_t)G * NW * (p.d + 4) + (size_t)G * NW) * 4;
+    const int sms = device_sm_count(f->device);
+    const int64_t n_tiles = (p.n_rows + G * NW - 1) / (G * NW);
+    const int grid = (int)std::min<int64_t>(n_tiles, sms);
+    IFB_CUDA(cudaFuncSetAttribute(score_ext_wide_kernel<G, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    score_ext_wide_kernel<G, NW><<<grid, NW * 32, smem, stream>>>(p);
+    IFB_CUDA(cudaGetLastError());
+    count_launch();
+    return IFB_OK;
+}
+
 }  // namespace
 
 int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
@@ -282,6 +519,7 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
         q.num_trees = f->num_trees; q.total_trees = f->num_trees; q.blob_max = f->ext_blob_max;
         q.avg_path = f->avg_path_norm; q.accumulate_only = accumulate_only ? 1 : 0;
         q.scores = scores; q.path_sum = path_sum; q.depth_sum = depth_sum;
+        q.k = f->max_nnz; q.w_safe = (f->ext_w_safe && getenv("IFB_EXT_NOSPLIT") == nullptr) ? 1 : 0; q.two29 = 0x20000000u; q.bias64 = 0x3800000000000000ull;
         int rc;
         switch (f->ext_blob_D) {
             case 8: rc = launch_dense<8>(f, q, stream); break;
@@ -290,6 +528,27 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
             default: rc = launch_dense<64>(f, q, stream); break;
         }
         if (rc >= 0) return rc;
+    }
+    if (f->ext_dense_identity && f->max_nnz == d && d > 64 && d % 4 == 0 && getenv("IFB_EXT_GENERIC") == nullptr) {
+        ScoreExtWideParams q;
+        q.X = X; q.n_rows = n_rows; q.ld = ld; q.d = d; q.layout = layout;
+        q.w = f->d_ext_w; q.off = f->d_ext_off; q.wabs = f->d_ext_wabs; q.leaf = f->d_ext_leaf;
+        q.child = f->d_ext_child; q.hp = f->d_ext_hp; q.tree_node = f->d_ext_tree_node;
+        q.num_trees = f->num_trees; q.total_trees = f->num_trees; q.rows_per_tile = 0;
+        q.avg_path = f->avg_path_norm; q.accumulate_only = accumulate_only ? 1 : 0;
+        q.scores = scores; q.path_sum = path_sum; q.depth_sum = depth_sum;
+        // rows per warp: as many as shared memory allows (<= 8), 8 warps per CTA
+        const size_t budget = (size_t)device_smem_optin(f->device) - 1024;
+        int G = (int)std::min<size_t>(8, budget / ((size_t)8 * ((size_t)d + 5) * 4));
+        if (G >= 1) {
+            switch (G) {
+                case 8: return launch_wide<8>(f, q, stream);
+                case 7: case 6: return launch_wide<6>(f, q, stream);
+                case 5: case 4: return launch_wide<4>(f, q, stream);
+                case 3: case 2: return launch_wide<2>(f, q, stream);
+                default: return launch_wide<1>(f, q, stream);
+            }
+        }
     }
     ScoreExtParams p;
     p.X = X;

@@ -75,7 +75,8 @@ def test_standard_synthetic(nat, oracle, dev, n, d, T):
 
 @pytest.mark.parametrize("n,d,T,ext", [(5_000, 8, 50, 0), (5_000, 8, 50, 3), (20_000, 64, 40, 63), (2_000, 200, 8, 199),
                                         (3_000, 40, 16, 9), (9_000, 16, 33, 15), (7_777, 32, 21, 31), (4_000, 24, 10, 23),
-                                        (300_000, 5, 12, 4), (1_000, 2, 7, 1)])
+                                        (300_000, 5, 12, 4), (1_000, 2, 7, 1), (3_000, 1024, 6, 1023), (5_000, 132, 10, 131),
+                                        (4_097, 68, 9, 67)])
 def test_extended_synthetic(nat, oracle, dev, n, d, T, ext):
     X = synth_mixture(n, d, 2000 + d)
     tables = oracle.fit_forest(X, T, 256, random_seed=1, ext_level=ext)
@@ -132,6 +133,50 @@ def test_special_values(nat, oracle, dev):
     Fe = nat.NativeForest.from_tables(te)
     refe = oracle.Forest(te).score(Xs, threads=4, want_parts=True)
     assert_parity(Fe.score_device(colmajor_cuda(Xs), want_parts=True), refe)
+
+
+def test_extended_dense_special_values_take_the_exact_path(nat, oracle, dev):
+    """The dense extended kernel widens part of the f32 products with integer ops when every lane of a warp has
+    'ordinary' features (finite, non-zero, 2^-60 <= |x| <= 2^60); rows with zeros, denormals, huge values, infs or
+    NaNs must fall back to the F2F path and still match the oracle bit for bit."""
+    n, d = 8192, 64
+    X = synth_mixture(n, d, 77)
+    te = oracle.fit_forest(X, 12, 256, random_seed=8, ext_level=d - 1)
+    Xs = X.copy()
+    Xs[3::64, 5] = 0.0                      # zero products (+0 / -0)
+    Xs[7::64, 9] = -0.0
+    Xs[11::64, 1] = np.float32(1e-42)       # denormal feature
+    Xs[13::64, 2] = np.float32(3e-38)       # tiny normal: product underflows to a denormal
+    Xs[17::64, 3] = np.float32(2e38)        # product overflows to inf
+    Xs[19::64, 4] = np.inf
+    Xs[23::64, 6] = np.nan
+    Xs[29::64, :] = 0.0                     # all-zero rows
+    F = nat.NativeForest.from_tables(te)
+    with np.errstate(all="ignore"):
+        ref = oracle.Forest(te).score(Xs, threads=8, want_parts=True)
+    assert_parity(F.score_device(colmajor_cuda(Xs), want_parts=True), ref)
+    # and the all-ordinary matrix (fast path everywhere) as well
+    assert_parity(F.score_device(colmajor_cuda(X), want_parts=True), oracle.Forest(te).score(X, threads=8, want_parts=True))
+
+
+def test_extended_wide_kernel_special_values(nat, oracle, dev):
+    """k = d > 64 runs the wide kernel (lanes split the terms; re-association guarded by a rounding bound with a
+    sequential fallback).  NaN / inf / overflow / exact-zero ties must come out exactly as the sequential oracle."""
+    n, d = 2048, 256
+    X = synth_mixture(n, d, 91)
+    te = oracle.fit_forest(X, 8, 256, random_seed=4, ext_level=d - 1)
+    Xs = X.copy()
+    Xs[5::32, 7] = np.nan
+    Xs[9::32, 100] = np.inf
+    Xs[13::32, 200] = -np.inf
+    Xs[17::32, :] = 0.0                      # sum == 0 exactly: zero tolerance => sequential path
+    Xs[21::32, 3] = np.float32(3e38)         # products overflow
+    Xs[25::32, :] *= np.float32(1e-30)       # tiny magnitudes
+    F = nat.NativeForest.from_tables(te)
+    with np.errstate(all="ignore"):
+        ref = oracle.Forest(te).score(Xs, threads=8, want_parts=True)
+    assert_parity(F.score_device(colmajor_cuda(Xs), want_parts=True), ref)
+    assert_parity(F.score_device(torch.from_numpy(Xs).cuda(), want_parts=True), ref)
 
 
 def test_threshold_boundary_values(nat, oracle, dev):
