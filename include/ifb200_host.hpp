@@ -23,12 +23,14 @@
 #include <string>
 #include <vector>
 
+#define IFBH_CLASS __attribute__((visibility("default")))
+
 namespace ifb200 {
 
-struct IllegalArgumentException : std::invalid_argument {
+struct IFBH_CLASS IllegalArgumentException : std::invalid_argument {
     using std::invalid_argument::invalid_argument;
 };
-struct IllegalStateException : std::logic_error {
+struct IFBH_CLASS IllegalStateException : std::logic_error {
     using std::logic_error::logic_error;
 };
 
@@ -60,7 +62,7 @@ struct ForestTables {
 };
 
 // IsolationForestParamsBase (+ extensionLevel of ExtendedIsolationForestParams).
-class ForestParams {
+class IFBH_CLASS ForestParams {
    public:
     ForestParams &setNumEstimators(int v);
     ForestParams &setMaxSamples(double v);
@@ -113,7 +115,7 @@ class ForestParams {
     friend class ForestEstimatorBase;
 };
 
-class ForestModelBase : public ForestParams {
+class IFBH_CLASS ForestModelBase : public ForestParams {
    public:
     virtual ~ForestModelBase();
     ForestModelBase(const ForestModelBase &) = delete;
@@ -149,7 +151,7 @@ class ForestModelBase : public ForestParams {
     friend class ForestEstimatorBase;
 };
 
-class IsolationForestModel final : public ForestModelBase {
+class IFBH_CLASS IsolationForestModel final : public ForestModelBase {
    public:
     static constexpr int UnknownTotalNumFeatures = -1;
     // new IsolationForestModel(uid, trees, numSamples, numFeatures[, totalNumFeatures])
@@ -158,14 +160,14 @@ class IsolationForestModel final : public ForestModelBase {
     static std::unique_ptr<IsolationForestModel> load(const std::string &path, int device = 0);
 };
 
-class ExtendedIsolationForestModel final : public ForestModelBase {
+class IFBH_CLASS ExtendedIsolationForestModel final : public ForestModelBase {
    public:
     ExtendedIsolationForestModel(std::string uid, ForestTables trees, int numSamples, int numFeatures,
                                  int totalNumFeatures, int device = 0);
     static std::unique_ptr<ExtendedIsolationForestModel> load(const std::string &path, int device = 0);
 };
 
-class ForestEstimatorBase : public ForestParams {
+class IFBH_CLASS ForestEstimatorBase : public ForestParams {
    public:
     const std::string &uid() const { return uid_; }
 
@@ -176,14 +178,14 @@ class ForestEstimatorBase : public ForestParams {
     std::string uid_;
 };
 
-class IsolationForest final : public ForestEstimatorBase {
+class IFBH_CLASS IsolationForest final : public ForestEstimatorBase {
    public:
     IsolationForest();                           // Identifiable.randomUID("isolation-forest")
     explicit IsolationForest(std::string uid);
     std::unique_ptr<IsolationForestModel> fit(const FeatureMatrix &data) const;   // IF/IsolationForest.scala:46
 };
 
-class ExtendedIsolationForest final : public ForestEstimatorBase {
+class IFBH_CLASS ExtendedIsolationForest final : public ForestEstimatorBase {
    public:
     ExtendedIsolationForest();                   // randomUID("extended-isolation-forest")
     explicit ExtendedIsolationForest(std::string uid);
@@ -195,7 +197,7 @@ struct ResolvedParams {
     int numFeatures, totalNumFeatures, numSamples;
     int64_t totalNumSamples;
 };
-ResolvedParams validateAndResolveParams(int64_t totalNumSamples, int totalNumFeatures, double maxFeatures,
+IFBH_CLASS ResolvedParams validateAndResolveParams(int64_t totalNumSamples, int totalNumFeatures, double maxFeatures,
                                         double maxSamples);
 
 }  // namespace ifb200

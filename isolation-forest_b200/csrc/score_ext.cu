@@ -177,7 +177,7 @@ __device__ __forceinline__ double widen_int(float pf, uint32_t two29, uint64_t b
 
 // One thread owns one row, held in registers (D floats, zero padded); the trees stream through a 2-slot
 // shared-memory ring, one self-contained blob per tree (forest.cu::build_extended_tables).
-template <int D, int R>
+template <int D, int R, int NI>
 __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseParams p) {
     extern __shared__ __align__(128) unsigned char smem_e[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_e);
@@ -248,11 +248,13 @@ __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseP
 #pragma unroll
                     for (int q = 0; q < D / 4; q++) {
                         const float4 w4 = wp[q];
-                        // same values, same order; terms 1 and 3 of each quad are widened on the ALU/FMA pipes
-                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.x, xr[4 * q + 0]));
-                        sum = __dadd_rn(sum, widen_int(__fmul_rn(w4.y, xr[4 * q + 1]), two29, bias64));
-                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.z, xr[4 * q + 2]));
-                        sum = __dadd_rn(sum, widen_int(__fmul_rn(w4.w, xr[4 * q + 3]), two29, bias64));
+                        // same values, same order; NI of the 4 terms of a quad are widened on the ALU/FMA pipes
+                        const float p0 = __fmul_rn(w4.x, xr[4 * q + 0]), p1 = __fmul_rn(w4.y, xr[4 * q + 1]);
+                        const float p2 = __fmul_rn(w4.z, xr[4 * q + 2]), p3 = __fmul_rn(w4.w, xr[4 * q + 3]);
+                        sum = __dadd_rn(sum, NI >= 4 ? widen_int(p0, two29, bias64) : (double)p0);
+                        sum = __dadd_rn(sum, NI >= 1 ? widen_int(p1, two29, bias64) : (double)p1);
+                        sum = __dadd_rn(sum, NI >= 3 ? widen_int(p2, two29, bias64) : (double)p2);
+                        sum = __dadd_rn(sum, NI >= 2 ? widen_int(p3, two29, bias64) : (double)p3);
                     }
                 } else {
 #pragma unroll
@@ -296,8 +298,19 @@ int launch_dense(const ifb_forest *f, const ScoreExtDenseParams &p, cudaStream_t
     per_sm = std::max(per_sm, 1);
     const int64_t n_tiles = (p.n_rows + R - 1) / R;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm);
-    IFB_CUDA(cudaFuncSetAttribute(score_ext_dense_kernel<D, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    score_ext_dense_kernel<D, R><<<grid, R, smem, stream>>>(p);
+    static const int ni = getenv("IFB_EXT_NI") ? atoi(getenv("IFB_EXT_NI")) : 1;
+    auto go = [&](auto kern) -> int {
+        IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, R, smem, stream>>>(p);
+        return IFB_OK;
+    };
+    int rc;
+    if (ni == 1) rc = go(score_ext_dense_kernel<D, R, 1>);
+    else if (ni == 3) rc = go(score_ext_dense_kernel<D, R, 3>);
+    else if (ni == 4) rc = go(score_ext_dense_kernel<D, R, 4>);
+    else if (ni == 2) rc = go(score_ext_dense_kernel<D, R, 2>);
+    else rc = go(score_ext_dense_kernel<D, R, 1>);
+    if (rc) return rc;
     IFB_CUDA(cudaGetLastError());
     count_launch();
     return IFB_OK;
@@ -413,22 +426,34 @@ __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtW
                     const int64_t gn = base + n0;
                     const int32_t slot = __ldg(p.hp + gn);
                     const float *wrow = p.w + (int64_t)slot * d;
-                    double acc[G];
+                    // four independent f64 chains per (lane, row): the order is already covered by the bound below
+                    double acc[G][4];
 #pragma unroll
-                    for (int g = 0; g < G; g++) acc[g] = 0.0;
-                    for (int j = 0; j < chunks; j++) {
-                        const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wrow + j * 128) + lane);
+                    for (int g = 0; g < G; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.0;
+                    // weight chunks are fetched PB at a time (independent 512-byte coalesced loads in flight per
+                    // warp) before any arithmetic touches them: the forest lives in L2, not in shared memory
+                    constexpr int PB = 8;
+                    for (int jb = 0; jb < chunks; jb += PB) {
+                        float4 wv[PB];
 #pragma unroll
-                        for (int g = 0; g < G; g++) {
-                            if ((grp >> g) & 1u) {
-                                const float4 x4 = *reinterpret_cast<const float4 *>(
-                                    xs_w + (size_t)(warp * G + g) * xstride + j * 128 + lane * 4);
-                                double a = acc[g];
-                                a = __dadd_rn(a, (double)__fmul_rn(w4.x, x4.x));
-                                a = __dadd_rn(a, (double)__fmul_rn(w4.y, x4.y));
-                                a = __dadd_rn(a, (double)__fmul_rn(w4.z, x4.z));
-                                a = __dadd_rn(a, (double)__fmul_rn(w4.w, x4.w));
-                                acc[g] = a;
+                        for (int u = 0; u < PB; u++)
+                            if (jb + u < chunks)
+                                wv[u] = __ldg(reinterpret_cast<const float4 *>(wrow + (jb + u) * 128) + lane);
+#pragma unroll
+                        for (int u = 0; u < PB; u++) {
+                            if (jb + u < chunks) {
+                                const float4 w4 = wv[u];
+#pragma unroll
+                                for (int g = 0; g < G; g++) {
+                                    if ((grp >> g) & 1u) {
+                                        const float4 x4 = *reinterpret_cast<const float4 *>(
+                                            xs_w + (size_t)(warp * G + g) * xstride + (jb + u) * 128 + lane * 4);
+                                        acc[g][0] = __dadd_rn(acc[g][0], (double)__fmul_rn(w4.x, x4.x));
+                                        acc[g][1] = __dadd_rn(acc[g][1], (double)__fmul_rn(w4.y, x4.y));
+                                        acc[g][2] = __dadd_rn(acc[g][2], (double)__fmul_rn(w4.z, x4.z));
+                                        acc[g][3] = __dadd_rn(acc[g][3], (double)__fmul_rn(w4.w, x4.w));
+                                    }
+                                }
                             }
                         }
                     }
@@ -437,7 +462,7 @@ __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtW
 #pragma unroll
                         for (int g = 0; g < G; g++)
                             if ((grp >> g) & 1u)
-                                acc[g] = __dadd_rn(acc[g], (double)__fmul_rn(wv, xs_w[(size_t)(warp * G + g) * xstride + i]));
+                                acc[g][0] = __dadd_rn(acc[g][0], (double)__fmul_rn(wv, xs_w[(size_t)(warp * G + g) * xstride + i]));
                     }
                     const double offv = __ldg(p.off + gn);
                     const double wabs = __ldg(p.wabs + slot);
@@ -445,7 +470,7 @@ __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtW
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         if ((grp >> g) & 1u) {
-                            double v = acc[g];
+                            double v = __dadd_rn(__dadd_rn(acc[g][0], acc[g][1]), __dadd_rn(acc[g][2], acc[g][3]));
                             for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
                             v = __shfl_sync(0xffffffffu, v, 0);
                             const double A = (double)rowmax[warp * G + g] * wabs * 1.0000002;
@@ -490,7 +515,7 @@ __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtW
 
 template <int G>
 int launch_wide(const ifb_forest *f, const ScoreExtWideParams &p0, cudaStream_t stream) {
-    constexpr int NW = 8;
+    constexpr int NW = 16;
     ScoreExtWideParams p = p0;
     p.rows_per_tile = G * NW;
     const size_t smem = ((size_t)G * NW * (p.d + 4) + (size_t)G * NW) * 4;
@@ -537,15 +562,14 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
         q.num_trees = f->num_trees; q.total_trees = f->num_trees; q.rows_per_tile = 0;
         q.avg_path = f->avg_path_norm; q.accumulate_only = accumulate_only ? 1 : 0;
         q.scores = scores; q.path_sum = path_sum; q.depth_sum = depth_sum;
-        // rows per warp: as many as shared memory allows (<= 8), 8 warps per CTA
+        // rows per warp: as many as shared memory allows (<= 4), 16 warps per CTA
         const size_t budget = (size_t)device_smem_optin(f->device) - 1024;
-        int G = (int)std::min<size_t>(8, budget / ((size_t)8 * ((size_t)d + 5) * 4));
+        int G = (int)std::min<size_t>(4, budget / ((size_t)16 * ((size_t)d + 5) * 4));
         if (G >= 1) {
             switch (G) {
-                case 8: return launch_wide<8>(f, q, stream);
-                case 7: case 6: return launch_wide<6>(f, q, stream);
-                case 5: case 4: return launch_wide<4>(f, q, stream);
-                case 3: case 2: return launch_wide<2>(f, q, stream);
+                case 4: return launch_wide<4>(f, q, stream);
+                case 3: return launch_wide<3>(f, q, stream);
+                case 2: return launch_wide<2>(f, q, stream);
                 default: return launch_wide<1>(f, q, stream);
             }
         }

@@ -143,3 +143,20 @@ def test_fit_is_deterministic_and_matches_oracle(pkg, oracle, mammography):
     ref = oracle.fit_forest(X.astype(np.float32), 30, 256, random_seed=11)
     for k in ("node_off", "left", "right", "feature", "threshold", "num_instances"):
         assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], ref[k]), k
+
+
+def test_cpp_host_program(pkg, tmp_path):
+    """The C++ API used directly (no Python in between): tests/cpp/host_roundtrip.cpp."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    lib = os.path.join(ROOT, "isolation-forest_b200")
+    exe = tmp_path / "host_roundtrip"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "host_roundtrip.cpp"), "-o", str(exe), "-L" + lib,
+                           "-lifb200_host", "-lifb200", "-Wl,-rpath," + lib])
+    out = subprocess.run([str(exe), str(tmp_path / "model")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "host_roundtrip ok" in out.stdout
