@@ -189,6 +189,8 @@ class NativeForest:
         """(n, d, ld, layout) of a 2-D (rows x features) view given element strides."""
         n, d = x_shape
         rs, cs = strides_elems
+        if n == 0:
+            return 0, d, d, ROW_MAJOR
         if cs == 1 and (rs >= d or n <= 1):
             return n, d, max(rs, d) if n > 1 else d, ROW_MAJOR
         if rs == 1 and (cs >= n or d <= 1):

@@ -311,3 +311,37 @@ def test_full_size_properties(nat, oracle, dev):
     assert torch.equal(s2, s[lo:hi])
     # no-depth instantiation == depth instantiation
     assert torch.equal(F.score_device(X), s)
+
+
+def test_concurrent_scoring_on_a_shared_forest(nat, oracle, dev):
+    """A forest handle is immutable and shared by every executor task thread in the reference
+    (IF/IsolationForestModel.scala:129-142): ifb_score_host must be re-entrant on one handle."""
+    import threading
+
+    n, d = 200_000, 16
+    X = synth_mixture(n, d, 55)
+    tables = oracle.fit_forest(X, 40, 256, random_seed=6)
+    F = nat.NativeForest.from_tables(tables)
+    ref = oracle.Forest(tables).score(X, threads=8)
+    parts = [np.ascontiguousarray(X[i::8]) for i in range(8)]
+    out = [None] * 8
+
+    def work(i):
+        for _ in range(3):
+            out[i] = F.score_host(parts[i])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(8):
+        assert np.max(np.abs(out[i] - ref[i::8]) / ref[i::8]) <= 1e-12
+
+
+def test_empty_and_tiny_inputs(nat, oracle, dev):
+    X = synth_mixture(1000, 7, 2)
+    tables = oracle.fit_forest(X, 10, 64, random_seed=1)
+    F = nat.NativeForest.from_tables(tables)
+    assert F.score_host(np.zeros((0, 7), np.float32)).shape == (0,)
+    assert F.score_device(torch.zeros(0, 7, device="cuda")).shape == (0,)
+    one = F.score_host(X[:1])
+    assert one[0] == oracle.Forest(tables).score(X[:1])[0] or abs(one[0] / oracle.Forest(tables).score(X[:1])[0] - 1) < 1e-12
