@@ -6,6 +6,7 @@
 #include <cstring>
 #include <filesystem>
 #include <functional>
+#include <mutex>
 #include <fstream>
 #include <random>
 #include <sstream>
@@ -47,27 +48,74 @@ std::string randomUID(const std::string &prefix) {
 
 std::string fmtDouble(double v) { return json::javaDouble(v); }
 
-// f64 -> f32 (`.toFloat`, round to nearest even) into a pinned staging buffer, split over a few threads
+// Pinned staging buffers are expensive to create (cudaHostAlloc pins pages): keep a small process-wide pool.
+class PinnedPool {
+   public:
+    static PinnedPool &get() {
+        static PinnedPool p;
+        return p;
+    }
+    void *acquire(size_t bytes, size_t *cap) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].second >= bytes && (best == free_.size() || free_[i].second < free_[best].second)) best = i;
+            if (best != free_.size()) {
+                auto e = free_[best];
+                free_.erase(free_.begin() + (long)best);
+                cached_ -= e.second;
+                *cap = e.second;
+                return e.first;
+            }
+        }
+        void *p = nullptr;
+        const size_t want = std::max<size_t>(bytes, 1 << 20);
+        check(ifb_host_alloc(want, &p));
+        *cap = want;
+        return p;
+    }
+    void release(void *p, size_t cap) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (cached_ + cap > kMaxCached) {
+            ifb_host_free(p);
+            return;
+        }
+        free_.emplace_back(p, cap);
+        cached_ += cap;
+    }
+
+   private:
+    static constexpr size_t kMaxCached = (size_t)3 << 30;
+    std::mutex mu_;
+    std::vector<std::pair<void *, size_t>> free_;
+    size_t cached_ = 0;
+};
+
 struct Pinned {
     void *p = nullptr;
-    explicit Pinned(size_t bytes) { check(ifb_host_alloc(bytes, &p)); }
-    ~Pinned() { ifb_host_free(p); }
+    size_t cap = 0;
+    explicit Pinned(size_t bytes) { p = PinnedPool::get().acquire(bytes, &cap); }
+    ~Pinned() { PinnedPool::get().release(p, cap); }
     Pinned(const Pinned &) = delete;
 };
 
-void castRows(const FeatureMatrix &m, float *dst) {
-    const int64_t total = m.rows * (int64_t)m.cols;
-    if (m.f32) {
-        std::memcpy(dst, m.f32, (size_t)total * 4);
-        return;
-    }
-    const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, total / (1 << 22)), 16);
+// f64 -> f32 (`.toFloat`, round to nearest even) of rows [r0, r1) into a staging buffer, split over threads
+void castRows(const FeatureMatrix &m, int64_t r0, int64_t r1, float *dst) {
+    const int64_t off = r0 * (int64_t)m.cols, total = (r1 - r0) * (int64_t)m.cols;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, total / (1 << 20)), std::min(32u, hw));
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) {
         const int64_t a = total * t / nt, b = total * (t + 1) / nt;
-        th.emplace_back([=]() {
-            for (int64_t i = a; i < b; i++) dst[i] = (float)m.f64[i];
-        });
+        if (m.f32) {
+            th.emplace_back([=]() { std::memcpy(dst + a, m.f32 + off + a, (size_t)(b - a) * 4); });
+        } else {
+            th.emplace_back([=]() {
+                const double *src = m.f64 + off;
+                for (int64_t i = a; i < b; i++) dst[i] = (float)src[i];
+            });
+        }
     }
     for (auto &x : th) x.join();
 }
@@ -259,10 +307,26 @@ ScoredData ForestModelBase::transform(const FeatureMatrix &data) const {
     out.predictedLabel.assign((size_t)data.rows, 0.0);
     if (data.rows == 0) return out;
     ifb_forest *f = (ifb_forest *)native();
-    Pinned stage((size_t)data.rows * data.cols * 4);
-    castRows(data, (float *)stage.p);
-    check(ifb_score_host(f, (const float *)stage.p, data.rows, data.cols, data.cols, IFB_ROW_MAJOR, out.outlierScore.data(),
-                         nullptr, nullptr));
+    // batches of rows: while batch k is on the GPU (ifb_score_host pipelines its own H2D / kernel / D2H sub-chunks),
+    // a helper thread casts batch k+1 (`.toFloat`) into the other pinned staging buffer
+    const int64_t batch = std::max<int64_t>(1 << 16, std::min<int64_t>(data.rows, ((int64_t)256 << 20) / (4LL * data.cols)));
+    const int64_t n_batches = (data.rows + batch - 1) / batch;
+    Pinned stage0((size_t)std::min(batch, data.rows) * data.cols * 4);
+    std::unique_ptr<Pinned> stage1;
+    if (n_batches > 1) stage1 = std::make_unique<Pinned>((size_t)batch * data.cols * 4);
+    Pinned sc((size_t)std::min(batch, data.rows) * 8);
+    auto buf = [&](int64_t k) { return (float *)((k & 1) ? stage1->p : stage0.p); };
+    castRows(data, 0, std::min(batch, data.rows), buf(0));
+    for (int64_t k = 0; k < n_batches; k++) {
+        const int64_t r0 = k * batch, r1 = std::min(data.rows, r0 + batch);
+        std::thread next;
+        if (k + 1 < n_batches)
+            next = std::thread([&, k]() { castRows(data, (k + 1) * batch, std::min(data.rows, (k + 2) * batch), buf(k + 1)); });
+        int rc = ifb_score_host(f, buf(k), r1 - r0, data.cols, data.cols, IFB_ROW_MAJOR, (double *)sc.p, nullptr, nullptr);
+        if (next.joinable()) next.join();
+        check(rc);
+        std::memcpy(out.outlierScore.data() + r0, sc.p, (size_t)(r1 - r0) * 8);
+    }
     if (outlierScoreThreshold_ > 0)  // :143-148
         for (int64_t i = 0; i < data.rows; i++) out.predictedLabel[i] = out.outlierScore[i] >= outlierScoreThreshold_ ? 1.0 : 0.0;
     return out;
@@ -463,9 +527,13 @@ std::unique_ptr<ForestModelBase> ForestEstimatorBase::fitImpl(const FeatureMatri
     const size_t elems = (size_t)data.rows * data.cols;
     DeviceBuf dX(device, elems * 4);
     {
-        Pinned stage(elems * 4);
-        castRows(data, (float *)stage.p);
-        check(ifb_copy_to_device(device, dX.p, stage.p, elems * 4));
+        const int64_t batch = std::max<int64_t>(1 << 16, std::min<int64_t>(data.rows, ((int64_t)256 << 20) / (4LL * data.cols)));
+        Pinned stage((size_t)std::min(batch, data.rows) * data.cols * 4);
+        for (int64_t r0 = 0; r0 < data.rows; r0 += batch) {
+            const int64_t r1 = std::min(data.rows, r0 + batch);
+            castRows(data, r0, r1, (float *)stage.p);
+            check(ifb_copy_to_device(device, (float *)dX.p + r0 * data.cols, stage.p, (size_t)(r1 - r0) * data.cols * 4));
+        }
     }
     ifb_fit_params fp;
     fp.num_estimators = numEstimators;
