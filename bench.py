@@ -188,7 +188,8 @@ def run_native(args, wl_name, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     nat = graft.load_package()._native
-    tree_sharded = args.shard == "trees" and world > 1
+    tree_sharded = args.shard in ("trees", "trees-fused") and world > 1
+    fused = args.shard == "trees-fused" and world > 1
 
     # ---- setup (untimed): forest from the product's own GPU fit on a rank-independent training matrix ----
     train = mixture_torch(torch, TRAIN_ROWS if n >= TRAIN_ROWS else max(n, ns), d, 4242, dev)
@@ -203,9 +204,16 @@ def run_native(args, wl_name, wl):
     X = mixture_torch(torch, n, d, 1002 + (0 if tree_sharded else rank), dev)
     scores = torch.empty(n, dtype=torch.float64, device=dev)
     psum = torch.zeros(n, dtype=torch.float32, device=dev) if tree_sharded else None
+    ctx = None
+    if fused:
+        from isolation_forest_b200 import distributed as D
+        ctx = D.ScatterContext(n)
+        scores = torch.empty(ctx.rows_local, dtype=torch.float64, device=dev)
 
     def step():
-        if tree_sharded:
+        if fused:
+            ctx.score(forest, X, T, ns, scores_local=scores)   # kernel scatters partial sums into peer memory
+        elif tree_sharded:
             psum.zero_()
             forest.score_partial_device(X, psum)
             dist.all_reduce(psum)                       # NCCL sum of per-row path-length sums over NVLink
@@ -286,7 +294,8 @@ def run_native(args, wl_name, wl):
         "data": "synthetic",
         "config": {"workload": f"{wl_name}: IsolationForestModel.transform {n}x{d} f32 per GPU, {T} trees, "
                                f"maxSamples={ns}" + (f", extensionLevel={ext}" if ext >= 0 else ""),
-                   "parallelism": (f"trees sharded x{world} + NCCL all-reduce of path sums" if tree_sharded else
+                   "parallelism": (f"trees sharded x{world}, partial sums scattered into NVLink peer memory by the scoring kernel"
+                                   if fused else f"trees sharded x{world} + NCCL all-reduce of path sums" if tree_sharded else
                                    f"rows sharded x{world}, forest replicated, no data-path collective"),
                    "l2": f"inputs ({n * d * 4 / 1e9:.2f} GB/GPU) larger than L2; no flush needed",
                    "forest": {"nodes": int(info.num_nodes), "max_depth": int(info.max_depth),
@@ -321,7 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
-    ap.add_argument("--shard", choices=["rows", "trees"], default="rows")
+    ap.add_argument("--shard", choices=["rows", "trees", "trees-fused"], default="rows")
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -148,6 +148,23 @@ IFB_API int ifb_finalize_scores_device(int32_t device, const float *path_sum, in
                                        int32_t total_num_trees, int32_t num_samples, double *scores,
                                        void *stream);
 
+/* Fused variant of the tree-sharded layout (no NCCL on the data path): rows are cut into `world` contiguous
+ * ownership ranges row_cuts[0..world]; rank r's scoring kernel writes its partial path-length sum of every row
+ * straight into the OWNER's buffer peer_partials[owner][r][row - row_cuts[owner]] -- plain stores to NVLink peer
+ * memory from the kernel's epilogue, i.e. a reduce-scatter fused into the compute kernel.  peer_partials[o] is
+ * rank o's buffer of world * rows_o floats, mapped into this process with ifb_ipc_open (o == rank: the local
+ * pointer).  After every rank's kernel has finished (stream sync + barrier), each owner calls
+ * ifb_finalize_gathered_device on its own buffer: partials are added in rank order (reproducible) and turned
+ * into scores with the full ensemble size.  Standard forests, column-major input. */
+IFB_API int ifb_ipc_export(int32_t device, void *device_ptr, void *handle64 /* 64 bytes out */);
+IFB_API int ifb_ipc_open(int32_t device, const void *handle64, void **device_ptr);
+IFB_API int ifb_ipc_close(int32_t device, void *device_ptr);
+IFB_API int ifb_score_scatter_device(const ifb_forest *forest, const float *X, int64_t n_rows, int32_t d, int64_t ld,
+                                     int32_t layout, int32_t world, int32_t rank, const int64_t *row_cuts /*[world+1]*/,
+                                     float *const *peer_partials /*[world]*/, void *stream);
+IFB_API int ifb_finalize_gathered_device(int32_t device, const float *partials, int32_t world, int64_t rows_local,
+                                         int32_t total_num_trees, int32_t num_samples, double *scores, void *stream);
+
 /* prediction column: (score >= threshold) ? 1.0 : 0.0, all 0.0 when threshold <= 0
  * (IF/IsolationForestModel.scala:143-148). */
 IFB_API int ifb_predict_device(int32_t device, const double *scores, int64_t n_rows, double threshold,

@@ -67,6 +67,13 @@ SYMBOLS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "ifb_finalize_scores_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                              C.c_void_p]),
+    "ifb_ipc_export": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p]),
+    "ifb_ipc_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ifb_ipc_close": (C.c_int, [C.c_int32, C.c_void_p]),
+    "ifb_score_scatter_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ifb_finalize_gathered_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                               C.c_void_p, C.c_void_p]),
     "ifb_predict_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
     "ifb_fit_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                  C.POINTER(FitParams), C.POINTER(C.c_void_p), C.c_void_p]),

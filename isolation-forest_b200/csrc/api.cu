@@ -121,6 +121,71 @@ int ifb_finalize_scores_device(int32_t device, const float *path_sum, int64_t n_
                            (cudaStream_t)stream);
 }
 
+// ---- fused tree-sharded scoring over peer memory ------------------------------------------------------
+int ifb_ipc_export(int32_t device, void *device_ptr, void *handle64) {
+    IFB_REQUIRE(device_ptr && handle64, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard dg(device);
+    IFB_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), device_ptr));
+    return IFB_OK;
+}
+int ifb_ipc_open(int32_t device, const void *handle64, void **device_ptr) {
+    IFB_REQUIRE(device_ptr && handle64, "null argument");
+    DeviceGuard dg(device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    IFB_CUDA(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return IFB_OK;
+}
+int ifb_ipc_close(int32_t device, void *device_ptr) {
+    DeviceGuard dg(device);
+    if (device_ptr) IFB_CUDA(cudaIpcCloseMemHandle(device_ptr));
+    return IFB_OK;
+}
+
+int ifb_score_scatter_device(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
+                             int32_t world, int32_t rank, const int64_t *row_cuts, float *const *peer_partials,
+                             void *stream) {
+    int rc = check_scoring_args(f, X, n_rows, d, ld, layout);
+    if (rc) return rc;
+    IFB_REQUIRE(!f->extended, "ifb_score_scatter_device supports standard forests (use ifb_score_partial_device + "
+                              "all-reduce for extended forests)");
+    IFB_REQUIRE(layout == IFB_COL_MAJOR, "ifb_score_scatter_device expects a column-major matrix");
+    IFB_REQUIRE(world >= 1 && world <= kMaxScatterRanks && rank >= 0 && rank < world, "bad world/rank %d/%d", world, rank);
+    IFB_REQUIRE(row_cuts && peer_partials, "null argument");
+    IFB_REQUIRE(row_cuts[0] == 0 && row_cuts[world] == n_rows, "row_cuts must cover [0, n_rows)");
+    ScatterTarget st;
+    st.world = world;
+    st.rank = rank;
+    for (int i = 0; i <= kMaxScatterRanks; i++) st.cut[i] = i <= world ? row_cuts[i] : n_rows;
+    for (int i = 0; i < world; i++) IFB_REQUIRE(st.cut[i] <= st.cut[i + 1], "row_cuts must be non-decreasing");
+    for (int i = 0; i < kMaxScatterRanks; i++) st.peer[i] = i < world ? peer_partials[i] : nullptr;
+    if (n_rows == 0) return IFB_OK;
+    DeviceGuard dg(f->device);
+    tune_mempool(f->device);
+    ifb_forest::StdPlan *plan = nullptr;
+    rc = get_std_plan(const_cast<ifb_forest *>(f), d, &plan);
+    if (rc) return rc;
+    float *tmp_sum = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (plan->chunks.size() > 1) IFB_CUDA(cudaMallocAsync((void **)&tmp_sum, (size_t)n_rows * 4, s));
+    // all chunks but the last accumulate locally; the last one scatters the finished sums
+    rc = launch_score_standard(f, plan, X, n_rows, d, ld, IFB_COL_MAJOR, nullptr, nullptr, tmp_sum, /*accumulate_only=*/false,
+                               s, &st);
+    if (tmp_sum) cudaFreeAsync(tmp_sum, s);
+    return rc;
+}
+
+int ifb_finalize_gathered_device(int32_t device, const float *partials, int32_t world, int64_t rows_local,
+                                 int32_t total_num_trees, int32_t num_samples, double *scores, void *stream) {
+    IFB_REQUIRE(num_samples >= 2, "Cannot score with numSamples=%d; expected numSamples >= 2.", num_samples);
+    IFB_REQUIRE(total_num_trees > 0 && world >= 1, "bad ensemble size / world");
+    IFB_REQUIRE(rows_local == 0 || (partials && scores), "null buffer");
+    DeviceGuard dg(device);
+    return launch_finalize_gathered(partials, world, rows_local, total_num_trees, avg_path_length_host(num_samples), scores,
+                                    (cudaStream_t)stream);
+}
+
 int ifb_predict_device(int32_t device, const double *scores, int64_t n_rows, double threshold, double *labels,
                        void *stream) {
     IFB_REQUIRE(n_rows == 0 || (scores && labels), "null buffer");

@@ -20,6 +20,19 @@ __global__ void finalize_kernel(const float *__restrict__ path_sum, int64_t n, f
     }
 }
 
+// Second half of the fused reduce-scatter: partial sums of `world` tree shards, added in RANK ORDER (a fixed,
+// reproducible order -- unlike a ring all-reduce), then the same epilogue.
+__global__ void finalize_gathered_kernel(const float *__restrict__ partials, int world, int64_t rows, float total_trees,
+                                         float avg_path, double *__restrict__ scores) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < world; r++) s = s + partials[(int64_t)r * rows + i];
+        const float e = __fdiv_rn(s, total_trees);
+        const float z = __fdiv_rn(-e, avg_path);
+        scores[i] = exp2((double)z);
+    }
+}
+
 // IF/IsolationForestModel.scala:143-148
 __global__ void predict_kernel(const double *__restrict__ scores, int64_t n, double thr, double *__restrict__ labels) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -113,6 +126,16 @@ int launch_finalize(const float *path_sum, int64_t n_rows, int32_t total_trees, 
     if (n_rows == 0) return IFB_OK;
     const int grid = (int)std::min<int64_t>((n_rows + 255) / 256, 148 * 16);
     finalize_kernel<<<grid, 256, 0, stream>>>(path_sum, n_rows, (float)total_trees, avg_path, scores);
+    IFB_CUDA(cudaGetLastError());
+    count_launch();
+    return IFB_OK;
+}
+
+int launch_finalize_gathered(const float *partials, int32_t world, int64_t rows_local, int32_t total_trees, float avg_path,
+                             double *scores, cudaStream_t stream) {
+    if (rows_local == 0) return IFB_OK;
+    const int grid = (int)std::min<int64_t>((rows_local + 255) / 256, 148 * 16);
+    finalize_gathered_kernel<<<grid, 256, 0, stream>>>(partials, world, rows_local, (float)total_trees, avg_path, scores);
     IFB_CUDA(cudaGetLastError());
     count_launch();
     return IFB_OK;

@@ -151,6 +151,15 @@ int build_standard_tables(ifb_forest *f);
 int build_extended_tables(ifb_forest *f);
 int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out);
 
+// tree-sharded multi-GPU scoring: the scoring kernel's epilogue writes this rank's per-row partial sums straight
+// into the buffer of the rank that owns the row (peer memory over NVLink) -- a reduce-scatter fused into the kernel
+constexpr int kMaxScatterRanks = 8;
+struct ScatterTarget {
+    int32_t world = 0, rank = 0;
+    int64_t cut[kMaxScatterRanks + 1];   // rows [cut[o], cut[o+1]) are owned by rank o
+    float *peer[kMaxScatterRanks];       // peer[o]: rank o's buffer [world][rows_o] (device pointer mapped here)
+};
+
 // score_std.cu
 size_t std_top_table_bytes();
 int std_top_table_max_trees();
@@ -158,7 +167,8 @@ void std_fill_top_table(void *dst, const float *val, const uint32_t *meta, const
                         int rows_per_box);
 int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const float *X, int64_t n_rows,
                           int32_t d, int64_t ld, int32_t layout, double *scores, int32_t *depth_sum,
-                          float *path_sum, bool accumulate_only, cudaStream_t stream);
+                          float *path_sum, bool accumulate_only, cudaStream_t stream,
+                          const ScatterTarget *scatter = nullptr);
 // score_ext.cu
 int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld,
                           int32_t layout, double *scores, int32_t *depth_sum, float *path_sum,
@@ -167,6 +177,8 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
 int launch_finalize(const float *path_sum, int64_t n_rows, int32_t total_trees, float avg_path, double *scores,
                     cudaStream_t stream);
 int launch_predict(const double *scores, int64_t n_rows, double threshold, double *labels, cudaStream_t stream);
+int launch_finalize_gathered(const float *partials, int32_t world, int64_t rows_local, int32_t total_trees, float avg_path,
+                             double *scores, cudaStream_t stream);
 int launch_transpose(const float *in, int64_t n, int32_t d, int64_t ld_in, float *out, int64_t ld_out,
                      cudaStream_t stream);
 int launch_select(const double *scores, int64_t n, int64_t rank0, double *value, unsigned long long *count_ge,

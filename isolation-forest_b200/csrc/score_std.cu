@@ -63,10 +63,12 @@ struct ScoreStdParams {
     float avg_path;          // c(numSamples)
     int32_t first_chunk;     // start sums at 0 instead of reading path_sum / depth_sum
     int32_t finalize;        // write scores
+    int32_t finalize_scatter;  // last chunk of a scatter launch
     double *scores;
     float *path_sum;         // may be null when first_chunk && finalize
     int32_t *depth_sum;      // may be null
     int64_t n_tiles;
+    ScatterTarget scatter;   // tree-sharded multi-GPU: where the finished per-row sums of the LAST chunk go
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -305,7 +307,17 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
                 const float z = __fdiv_rn(-e, p.avg_path);
                 p.scores[row] = exp2((double)z);
             }
-            if (p.path_sum) p.path_sum[row] = s;
+            if (p.scatter.world > 0 && p.finalize_scatter) {
+                // fused reduce-scatter: this rank's partial sum of row `row` lands in the owning rank's buffer
+                // (plain coalesced stores to NVLink peer memory; slot [rank][row - first row of the owner])
+                int o = 0;
+#pragma unroll
+                for (int q = 1; q < kMaxScatterRanks; q++) o += (q < p.scatter.world && row >= p.scatter.cut[q]) ? 1 : 0;
+                const int64_t r0 = p.scatter.cut[o], rows_o = p.scatter.cut[o + 1] - r0;
+                p.scatter.peer[o][(int64_t)p.scatter.rank * rows_o + (row - r0)] = s;
+            } else if (p.path_sum) {
+                p.path_sum[row] = s;
+            }
             if (WANT_DEPTH) p.depth_sum[row] = dsum;
         }
         __syncthreads();  // every read of this stage is done before it is refilled
@@ -400,7 +412,7 @@ void std_fill_top_table(void *dst, const float *val, const uint32_t *meta, const
 
 int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const float *X, int64_t n_rows, int32_t d,
                           int64_t ld, int32_t layout, double *scores, int32_t *depth_sum, float *path_sum,
-                          bool accumulate_only, cudaStream_t stream) {
+                          bool accumulate_only, cudaStream_t stream, const ScatterTarget *scatter) {
     IFB_REQUIRE(layout == IFB_COL_MAJOR, "launch_score_standard expects a column-major matrix");
     if (n_rows == 0) return IFB_OK;
     const int R = plan->rows_per_tile;
@@ -449,11 +461,13 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
         p.total_trees = f->num_trees;
         p.avg_path = f->avg_path_norm;
         p.first_chunk = (ci == 0 && !accumulate_only) ? 1 : 0;
-        p.finalize = (ci + 1 == n_chunks && !accumulate_only) ? 1 : 0;
+        p.finalize = (ci + 1 == n_chunks && !accumulate_only && !scatter) ? 1 : 0;
         p.scores = scores;
         p.path_sum = path_sum;
         p.depth_sum = depth_sum;
         p.n_tiles = n_tiles;
+        if (scatter) p.scatter = *scatter; else p.scatter.world = 0;
+        p.finalize_scatter = (scatter && ci + 1 == n_chunks) ? 1 : 0;
         const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, d);
         const TopTable &top = *reinterpret_cast<const TopTable *>(plan->h_top.data() + (size_t)ci * sizeof(TopTable));
         int rc;

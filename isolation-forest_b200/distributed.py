@@ -90,3 +90,78 @@ def score_tree_sharded(local_forest, X, total_num_trees: int, num_samples: int, 
         dist.all_reduce(dsum, group=group)
     scores = nat.finalize_scores_device(psum, total_num_trees, num_samples)
     return (scores, dsum, psum) if want_depth else scores
+
+
+class ScatterContext:
+    """Peer-memory buffers for the FUSED tree-sharded transform (include/ifb200.h: ifb_score_scatter_device).
+
+    Rank o owns rows [cut[o], cut[o+1]) and exposes a buffer of world * rows_o floats through CUDA IPC; every rank
+    maps every peer's buffer once.  A transform is then: one scoring kernel per rank whose epilogue stores each
+    row's partial path-length sum into the owner's buffer over NVLink, a barrier, and a rank-ordered sum + score
+    epilogue on the owner.  No NCCL on the data path (the barrier is a one-element collective)."""
+
+    def __init__(self, n_rows: int, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _native as nat
+
+        self.nat, self.group = nat, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.cuda.current_device()
+        self.n_rows = n_rows
+        self.cuts = [row_shard(n_rows, r, self.world)[0] for r in range(self.world)] + [n_rows]
+        self.rows_local = self.cuts[self.rank + 1] - self.cuts[self.rank]
+        p = C.c_void_p()
+        nat.check(nat.lib().ifb_device_alloc(self.device, max(4, self.world * self.rows_local * 4), C.byref(p)))
+        self.local_ptr = p
+        handle = C.create_string_buffer(64)
+        nat.check(nat.lib().ifb_ipc_export(self.device, p, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peers = []
+        for o in range(self.world):
+            if o == self.rank:
+                self.peers.append(p)
+            else:
+                q = C.c_void_p()
+                nat.check(nat.lib().ifb_ipc_open(self.device, C.create_string_buffer(handles[o], 64), C.byref(q)))
+                self.peers.append(q)
+        self._peer_arr = (C.c_void_p * self.world)(*[x.value for x in self.peers])
+        self._cut_arr = (C.c_int64 * (self.world + 1))(*self.cuts)
+
+    def score(self, local_forest, X, total_num_trees: int, num_samples: int, scores_local=None):
+        """Returns this rank's slice of the scores (rows cut[rank] .. cut[rank+1])."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        nat = self.nat
+        n, d, ld, layout = nat.NativeForest._layout_of(tuple(X.shape), tuple(X.stride()))
+        assert n == self.n_rows and layout == nat.COL_MAJOR
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        nat.check(nat.lib().ifb_score_scatter_device(local_forest.handle, C.c_void_p(X.data_ptr()), n, d, ld, layout,
+                                                     self.world, self.rank, self._cut_arr, self._peer_arr, st))
+        dist.barrier(group=self.group)   # stream-ordered: every rank's stores have landed before anyone reads
+        if scores_local is None:
+            scores_local = torch.empty(self.rows_local, dtype=torch.float64, device=X.device)
+        nat.check(nat.lib().ifb_finalize_gathered_device(self.device, self.local_ptr, self.world, self.rows_local,
+                                                         total_num_trees, num_samples,
+                                                         C.c_void_p(scores_local.data_ptr()), st))
+        return scores_local
+
+    def close(self):
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for o, q in enumerate(self.peers):
+            if o != self.rank:
+                self.nat.lib().ifb_ipc_close(self.device, q)
+        dist.barrier(group=self.group)
+        self.nat.lib().ifb_device_free(self.device, self.local_ptr)
+        self.peers = []

@@ -33,6 +33,17 @@ for ext, d, T, n in ((-1, 32, 100, 2_000_000), (15, 16, 40, 300_000)):
     rel = float(((s_sh - s_ref).abs() / s_ref).max())
     assert rel < 1e-6, rel
     r0, r1 = D.row_shard(n, rank, world)
+    if ext < 0:
+        ctx = D.ScatterContext(n)
+        s_fused = ctx.score(local_forest, X, T, 256)
+        torch.cuda.synchronize()
+        relf = float(((s_fused - s_ref[r0:r1]).abs() / s_ref[r0:r1]).max())
+        assert relf < 1e-6, relf
+        s_fused2 = ctx.score(local_forest, X, T, 256)          # rank-ordered sums: bitwise reproducible
+        assert torch.equal(s_fused, s_fused2)
+        ctx.close()
+        if rank == 0:
+            print(f"fused scatter ok: max rel {relf:.2e}", flush=True)
     s_rows = full.score_device(X[r0:r1])
     assert torch.equal(s_rows, s_ref[r0:r1]), "row sharding must be bit-identical"
     if rank == 0:
