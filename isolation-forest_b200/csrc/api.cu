@@ -64,8 +64,17 @@ int score_device_impl(const ifb_forest *f, const float *X, int64_t n_rows, int32
     ifb_forest::StdPlan *plan = nullptr;
     int rc = get_std_plan(const_cast<ifb_forest *>(f), d, &plan);
     if (rc) return rc;
-    float *xt = nullptr;
-    float *tmp_sum = nullptr;
+    if (!plan)  // no shared-memory plan for rows this wide: generic kernel, either layout
+        return launch_score_standard_generic(f, X, n_rows, d, ld, layout, scores, depth_sum, path_sum, accumulate_only, stream);
+    struct Scratch {   // stream-ordered scratch, released on every exit path
+        cudaStream_t s;
+        float *p = nullptr;
+        ~Scratch() {
+            if (p) cudaFreeAsync(p, s);
+        }
+    } xt_g{stream}, sum_g{stream};
+    float *&xt = xt_g.p;
+    float *&tmp_sum = sum_g.p;
     const float *Xc = X;
     int64_t ldc = ld;
     if (layout == IFB_ROW_MAJOR) {
@@ -79,11 +88,8 @@ int score_device_impl(const ifb_forest *f, const float *X, int64_t n_rows, int32
         IFB_CUDA(cudaMallocAsync((void **)&tmp_sum, (size_t)n_rows * 4, stream));
         path_sum = tmp_sum;
     }
-    rc = launch_score_standard(f, plan, Xc, n_rows, d, ldc, IFB_COL_MAJOR, scores, depth_sum, path_sum,
-                               accumulate_only, stream);
-    if (xt) cudaFreeAsync(xt, stream);
-    if (tmp_sum) cudaFreeAsync(tmp_sum, stream);
-    return rc;
+    return launch_score_standard(f, plan, Xc, n_rows, d, ldc, IFB_COL_MAJOR, scores, depth_sum, path_sum, accumulate_only,
+                                 stream);
 }
 
 }  // namespace
@@ -166,6 +172,7 @@ int ifb_score_scatter_device(const ifb_forest *f, const float *X, int64_t n_rows
     ifb_forest::StdPlan *plan = nullptr;
     rc = get_std_plan(const_cast<ifb_forest *>(f), d, &plan);
     if (rc) return rc;
+    IFB_REQUIRE(plan != nullptr, "ifb_score_scatter_device: rows of %d features are too wide for the fused kernel", d);
     float *tmp_sum = nullptr;
     cudaStream_t s = (cudaStream_t)stream;
     if (plan->chunks.size() > 1) IFB_CUDA(cudaMallocAsync((void **)&tmp_sum, (size_t)n_rows * 4, s));
@@ -225,24 +232,37 @@ int ifb_score_host(const ifb_forest *f, const float *X, int64_t n_rows, int32_t 
     chunk = std::max<int64_t>(chunk, 1 << 16);
     chunk = (chunk + 1023) & ~1023ll;
     chunk = std::min<int64_t>(chunk, (n_rows + 3) & ~3ll);
-    cudaStream_t st[kSlots];
-    float *dX[kSlots] = {nullptr, nullptr, nullptr};
-    double *dS[kSlots] = {nullptr, nullptr, nullptr};
-    int32_t *dD[kSlots] = {nullptr, nullptr, nullptr};
-    float *dP[kSlots] = {nullptr, nullptr, nullptr};
     const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
     const int slots = (int)std::min<int64_t>(kSlots, n_chunks);
-    auto cleanup = [&]() {
-        for (int i = 0; i < slots; i++) {
-            if (dX[i]) cudaFreeAsync(dX[i], st[i]);
-            if (dS[i]) cudaFreeAsync(dS[i], st[i]);
-            if (dD[i]) cudaFreeAsync(dD[i], st[i]);
-            if (dP[i]) cudaFreeAsync(dP[i], st[i]);
-            cudaStreamSynchronize(st[i]);
-            cudaStreamDestroy(st[i]);
+    // streams and stream-ordered scratch of this call; released on every exit path
+    struct Pipe {
+        cudaStream_t st[kSlots] = {};
+        bool live[kSlots] = {};
+        float *dX[kSlots] = {};
+        double *dS[kSlots] = {};
+        int32_t *dD[kSlots] = {};
+        float *dP[kSlots] = {};
+        ~Pipe() {
+            for (int i = 0; i < kSlots; i++) {
+                if (!live[i]) continue;
+                if (dX[i]) cudaFreeAsync(dX[i], st[i]);
+                if (dS[i]) cudaFreeAsync(dS[i], st[i]);
+                if (dD[i]) cudaFreeAsync(dD[i], st[i]);
+                if (dP[i]) cudaFreeAsync(dP[i], st[i]);
+                cudaStreamSynchronize(st[i]);
+                cudaStreamDestroy(st[i]);
+            }
         }
-    };
-    for (int i = 0; i < slots; i++) IFB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    } pipe;
+    cudaStream_t *st = pipe.st;
+    float **dX = pipe.dX;
+    double **dS = pipe.dS;
+    int32_t **dD = pipe.dD;
+    float **dP = pipe.dP;
+    for (int i = 0; i < slots; i++) {
+        IFB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        pipe.live[i] = true;
+    }
     for (int i = 0; i < slots; i++) {
         IFB_CUDA(cudaMallocAsync((void **)&dX[i], (size_t)chunk * d * 4, st[i]));
         IFB_CUDA(cudaMallocAsync((void **)&dS[i], (size_t)chunk * 8, st[i]));
@@ -291,7 +311,6 @@ int ifb_score_host(const ifb_forest *f, const float *X, int64_t n_rows, int32_t 
             rc = IFB_ECUDA;
         }
     }
-    cleanup();
     return rc;
 }
 

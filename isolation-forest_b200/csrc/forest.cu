@@ -288,7 +288,11 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
             *out = p;
             return IFB_OK;
         }
-    IFB_REQUIRE(d >= 1 && d <= 16382, "standard scoring supports 1 <= d <= 16382 features, got %d", d);
+    IFB_REQUIRE(d >= 1, "d must be >= 1, got %d", d);
+    if (d > 16382) {  // feature index no longer fits the 16-bit node encoding
+        *out = nullptr;
+        return IFB_OK;
+    }
     IFB_REQUIRE(f->max_feature_index < d, "forest reads feature index %d but the matrix has only %d columns",
                 f->max_feature_index, d);
     const int smem_max = device_smem_optin(f->device);
@@ -322,10 +326,10 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
                 break;
             }
     if (R == 0 && room_for(32) >= need_one) R = 32;
-    if (R == 0) {
+    if (R == 0) {  // rows too wide for two tile stages next to one tree: the generic kernel takes over
         delete p;
-        set_error("no shared-memory plan for d=%d (largest tree %lld nodes)", d, (long long)largest_tree);
-        return IFB_EINVAL;
+        *out = nullptr;
+        return IFB_OK;
     }
     p->rows_per_tile = R;
     const int64_t room = smem_max - overhead - 2LL * (d + 1) * R * 4;
@@ -391,6 +395,25 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
     return IFB_OK;
 }
 
+int ensure_std_generic_tables(ifb_forest *f) {
+    std::lock_guard<std::mutex> lk(f->plan_mu);
+    if (f->d_gval) return IFB_OK;
+    const size_t n = f->h_val.size();
+    std::vector<int32_t> feat(n);
+    for (size_t i = 0; i < n; i++) feat[i] = f->h_child[i] < 0 ? -1 : (int32_t)f->h_meta_feat[i];
+    DeviceGuard dg(f->device);
+    IFB_CUDA(cudaMalloc((void **)&f->d_gval, std::max<size_t>(16, n * 4)));
+    IFB_CUDA(cudaMalloc((void **)&f->d_gfeat, std::max<size_t>(16, n * 4)));
+    IFB_CUDA(cudaMalloc((void **)&f->d_gchild, std::max<size_t>(16, n * 4)));
+    IFB_CUDA(cudaMalloc((void **)&f->d_groot, (f->bfs_off.size()) * 4));
+    IFB_CUDA(cudaMemcpy(f->d_gval, f->h_val.data(), n * 4, cudaMemcpyHostToDevice));
+    IFB_CUDA(cudaMemcpy(f->d_gfeat, feat.data(), n * 4, cudaMemcpyHostToDevice));
+    IFB_CUDA(cudaMemcpy(f->d_gchild, f->h_child.data(), n * 4, cudaMemcpyHostToDevice));
+    IFB_CUDA(cudaMemcpy(f->d_groot, f->bfs_off.data(), f->bfs_off.size() * 4, cudaMemcpyHostToDevice));
+    f->device_bytes += (int64_t)(n * 12 + f->bfs_off.size() * 4);
+    return IFB_OK;
+}
+
 }  // namespace ifb
 
 ifb_forest::~ifb_forest() {
@@ -401,6 +424,10 @@ ifb_forest::~ifb_forest() {
         cudaFree(p->d_tree_root);
         delete p;
     }
+    cudaFree(d_gval);
+    cudaFree(d_gfeat);
+    cudaFree(d_gchild);
+    cudaFree(d_groot);
     cudaFree(d_ext_w);
     cudaFree(d_ext_idx);
     cudaFree(d_ext_off);

@@ -117,6 +117,11 @@ struct ifb_forest {
     };
     std::mutex plan_mu;
     std::vector<StdPlan *> std_plans;
+    // global-memory tables for the generic fallback kernel (rows too wide for a shared-memory plan); lazily built
+    float *d_gval = nullptr;        // [nodes] BFS order: threshold (f32 ceil) or leaf value
+    int32_t *d_gfeat = nullptr;     // [nodes] feature, -1 at leaves
+    int32_t *d_gchild = nullptr;    // [nodes] tree-local BFS index of the left child, -1 at leaves
+    int32_t *d_groot = nullptr;     // [T+1] first BFS node of each tree
 
     // ---- extended kernel layout ----
     // BFS order per tree; hyperplanes stored densely per internal node with a fixed width k = max_nnz.
@@ -149,7 +154,11 @@ namespace ifb {
 // forest.cu
 int build_standard_tables(ifb_forest *f);
 int build_extended_tables(ifb_forest *f);
-int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out);
+int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out);   // *out = nullptr: no smem plan, use generic
+int ensure_std_generic_tables(ifb_forest *f);
+int launch_score_standard_generic(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld,
+                                  int32_t layout, double *scores, int32_t *depth_sum, float *path_sum,
+                                  bool accumulate_only, cudaStream_t stream);
 
 // tree-sharded multi-GPU scoring: the scoring kernel's epilogue writes this rank's per-row partial sums straight
 // into the buffer of the rank that owns the row (peer memory over NVLink) -- a reduce-scatter fused into the kernel

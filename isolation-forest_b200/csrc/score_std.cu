@@ -385,6 +385,56 @@ int launch_variant(bool use_tma, bool want_depth, const CUtensorMap &m0, const C
 
 }  // namespace
 
+// Generic fallback: one thread per row, node tables and features straight from global memory (L2).  Used only when
+// a row tile of the matrix cannot share shared memory with even one tree (d beyond ~850 features).
+namespace {
+__global__ void score_std_generic_kernel(const float *__restrict__ X, int64_t n_rows, int64_t ld, int layout,
+                                         const float *__restrict__ val, const int32_t *__restrict__ feat,
+                                         const int32_t *__restrict__ child, const int32_t *__restrict__ root, int num_trees,
+                                         int total_trees, float avg_path, int accumulate_only, double *scores,
+                                         float *path_sum, int32_t *depth_sum) {
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n_rows; row += (int64_t)gridDim.x * blockDim.x) {
+        float s = accumulate_only ? path_sum[row] : 0.f;
+        int32_t dsum = (accumulate_only && depth_sum) ? depth_sum[row] : 0;
+        const int64_t rs = layout == IFB_COL_MAJOR ? 1 : ld, cs = layout == IFB_COL_MAJOR ? ld : 1;
+        for (int t = 0; t < num_trees; t++) {
+            const int32_t base = root[t];
+            int32_t node = 0;
+            int32_t c = __ldg(child + base);
+            while (c >= 0) {
+                const float x = __ldg(X + row * rs + (int64_t)__ldg(feat + base + node) * cs);
+                node = c + ((x < __ldg(val + base + node)) ? 0 : 1);
+                c = __ldg(child + base + node);
+                dsum++;
+            }
+            s = s + __ldg(val + base + node);
+        }
+        if (!accumulate_only) {
+            const float e = __fdiv_rn(s, (float)total_trees);
+            const float z = __fdiv_rn(-e, avg_path);
+            scores[row] = exp2((double)z);
+        }
+        if (path_sum) path_sum[row] = s;
+        if (depth_sum) depth_sum[row] = dsum;
+    }
+}
+}  // namespace
+
+int launch_score_standard_generic(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
+                                  double *scores, int32_t *depth_sum, float *path_sum, bool accumulate_only,
+                                  cudaStream_t stream) {
+    if (n_rows == 0) return IFB_OK;
+    int rc = ensure_std_generic_tables(const_cast<ifb_forest *>(f));
+    if (rc) return rc;
+    const int grid = (int)std::min<int64_t>((n_rows + 127) / 128, (int64_t)device_sm_count(f->device) * 16);
+    score_std_generic_kernel<<<grid, 128, 0, stream>>>(X, n_rows, ld, layout, f->d_gval, f->d_gfeat, f->d_gchild, f->d_groot,
+                                                       f->num_trees, f->num_trees, f->avg_path_norm, accumulate_only ? 1 : 0,
+                                                       scores, path_sum, depth_sum);
+    IFB_CUDA(cudaGetLastError());
+    count_launch();
+    return IFB_OK;
+}
+
 size_t std_top_table_bytes() { return sizeof(TopTable); }
 int std_top_table_max_trees() { return kMaxTopTrees; }
 

@@ -61,7 +61,8 @@ def test_saved_models(nat, oracle, golden, dev, name, data):
 
 
 @pytest.mark.parametrize("n,d,T", [(1000, 10, 100), (50_000, 32, 100), (20_000, 64, 37), (8_192, 128, 512),
-                                   (3_000, 300, 64), (777, 1, 5), (5, 3, 3)])
+                                   (3_000, 300, 64), (777, 1, 5), (5, 3, 3), (2_000, 700, 40), (1_500, 1200, 30),
+                                   (600, 4000, 12)])
 def test_standard_synthetic(nat, oracle, dev, n, d, T):
     X = synth_mixture(n, d, 1000 + d)
     ns = min(256, n)
