@@ -211,16 +211,54 @@ int build_extended_tables(ifb_forest *f) {
     if ((rc = up((void **)&f->d_ext_hp, hp.data(), hp.size() * 4))) return rc;
     if ((rc = up((void **)&f->d_ext_len, len.data(), len.size() * 4))) return rc;
     {
-        std::vector<double> wabs((size_t)internal, 0.0);
+        std::vector<double> wabs((size_t)internal, 0.0), wnorm((size_t)internal, 0.0);
         for (int64_t sl = 0; sl < internal; sl++) {
-            double a = 0.0;
-            for (int i = 0; i < k; i++) a += std::fabs((double)w[(size_t)sl * k + i]);
+            double a = 0.0, q = 0.0;
+            for (int i = 0; i < k; i++) {
+                const double v = (double)w[(size_t)sl * k + i];
+                a += std::fabs(v);
+                q += v * v;
+            }
             wabs[(size_t)sl] = a;
+            wnorm[(size_t)sl] = std::sqrt(q) * 1.0000001;
         }
         if ((rc = up((void **)&f->d_ext_wabs, wabs.data(), wabs.size() * 8))) return rc;
+        if ((rc = up((void **)&f->d_ext_wnorm, wnorm.data(), wnorm.size() * 8))) return rc;
+        std::vector<WideNode> wn((size_t)total);
+        std::vector<int32_t> tslot((size_t)std::max(T, 1), -1);
+        for (int t = 0; t < T; t++) {
+            const int64_t base = f->node_off[t];
+            const int n = f->node_off[t + 1] - f->node_off[t];
+            tslot[t] = hp[base];
+            for (int q = 0; q < n; q++) {
+                const int64_t g = base + q;
+                WideNode &r = wn[(size_t)g];
+                r.off = off[g];
+                r.leaf = leaf[g];
+                r.cbase = child[g];
+                r.slot = hp[g];
+                r.slot_l = r.slot_r = -1;
+                r.wnorm = 0.f;
+                if (child[g] >= 0) {
+                    r.slot_l = hp[base + child[g]];
+                    r.slot_r = hp[base + child[g] + 1];
+                    float wf = (float)wnorm[(size_t)hp[g]];
+                    if ((double)wf < wnorm[(size_t)hp[g]]) wf = std::nextafterf(wf, INFINITY);
+                    r.wnorm = wf;
+                }
+            }
+        }
+        if ((rc = up((void **)&f->d_ext_wide_nodes, wn.data(), wn.size() * sizeof(WideNode)))) return rc;
+        if ((rc = up((void **)&f->d_ext_tree_slot, tslot.data(), tslot.size() * 4))) return rc;
     }
     if ((rc = up((void **)&f->d_ext_tree_node, tree_node.data(), tree_node.size() * 8))) return rc;
 
+    {
+        bool wsafe = true;   // finite and |w| <= 2^40: precondition of the f32 fast paths
+        for (float wv : w)
+            if (!(std::fabs(wv) <= 0x1p40f)) wsafe = false;
+        f->ext_w_safe = wsafe;
+    }
     // ---- per-tree blobs for the dense kernel ----
     if (f->ext_dense_identity && k <= 64) {
         const int D = k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64;
@@ -234,7 +272,7 @@ int build_extended_tables(ifb_forest *f) {
             int ni = 0;
             for (int q = 0; q < n; q++) ni += (child[base + q] >= 0);
             const int npad = (n + 3) & ~3, ipad = (ni + 1) & ~1;
-            const size_t bytes = 16 + (size_t)npad * 12 + (size_t)ipad * 8 + (size_t)ni * WS * 4;
+            const size_t bytes = 16 + (size_t)npad * 12 + (size_t)ipad * 16 + (size_t)ni * WS * 4;
             const size_t bpad = (bytes + 15) & ~(size_t)15;
             const size_t at = blob.size();
             blob.resize(at + bpad, 0);
@@ -244,7 +282,8 @@ int build_extended_tables(ifb_forest *f) {
             int32_t *bchild = (int32_t *)(B + 16), *bslot = bchild + npad;
             float *bleaf = (float *)(bslot + npad);
             double *boffs = (double *)(bleaf + npad);
-            float *bw = (float *)(boffs + ipad);
+            double *bwn = boffs + ipad;            // ||w||_2 of the slot, inflated: bound of the f32 fast path
+            float *bw = (float *)(bwn + ipad);
             int sl = 0;
             for (int q = 0; q < n; q++) {
                 const int64_t g = base + q;
@@ -254,7 +293,12 @@ int build_extended_tables(ifb_forest *f) {
                     bslot[q] = sl;
                     boffs[sl] = off[g];
                     const int64_t src = (int64_t)hp[g] * k;
-                    for (int i = 0; i < k; i++) bw[(size_t)sl * WS + i] = w[src + i];
+                    double sq = 0.0;
+                    for (int i = 0; i < k; i++) {
+                        bw[(size_t)sl * WS + i] = w[src + i];
+                        sq += (double)w[src + i] * (double)w[src + i];
+                    }
+                    bwn[sl] = std::sqrt(sq) * 1.0000001;
                     sl++;
                 } else {
                     bslot[q] = -1;
@@ -265,12 +309,7 @@ int build_extended_tables(ifb_forest *f) {
         }
         f->ext_blob_D = D;
         f->ext_blob_max = mx;
-        bool wsafe = true;
-        for (float wv : w) {
-            const float a = std::fabs(wv);
-            if (!(a >= 0x1p-60f && a <= 0x1p40f)) wsafe = false;
-        }
-        f->ext_w_safe = wsafe;
+
         if ((rc = up((void **)&f->d_ext_blob, blob.data(), blob.size()))) return rc;
         if ((rc = up((void **)&f->d_ext_blob_off, boff.data(), boff.size() * 8))) return rc;
     }
@@ -436,6 +475,9 @@ ifb_forest::~ifb_forest() {
     cudaFree(d_ext_hp);
     cudaFree(d_ext_len);
     cudaFree(d_ext_wabs);
+    cudaFree(d_ext_wnorm);
+    cudaFree(d_ext_wide_nodes);
+    cudaFree(d_ext_tree_slot);
     cudaFree(d_ext_tree_node);
     cudaFree(d_ext_blob);
     cudaFree(d_ext_blob_off);

@@ -70,6 +70,18 @@ struct StdChunk {
     int32_t node_begin = 0, node_count = 0;  // slice of the device arrays (node_count includes 1 pad slot)
 };
 
+// Node record of the wide extended kernel: everything a visit needs in one 32-byte load, including the weight
+// slots of BOTH children, so the next node's weight row can be requested as soon as the decision is known.
+struct WideNode {
+    double off;        // split offset (internal)
+    float wnorm;       // ||w||_2 inflated, rounded up to f32 (bound of the f32 tier)
+    float leaf;        // (float)depth + c(numInstances) at leaves
+    int32_t cbase;     // tree-local BFS index of the left child, -1 at leaves
+    int32_t slot_l;    // weight slot of the left child (-1: it is a leaf)
+    int32_t slot_r;    // weight slot of the right child
+    int32_t slot;      // own weight slot (-1 at leaves)
+};
+
 struct ExtTreeDesc {          // one per tree, extended forests
     int64_t node_begin;       // first node (BFS order) in the device arrays
     int32_t node_count;
@@ -133,6 +145,9 @@ struct ifb_forest {
     int32_t *d_ext_hp = nullptr;       // [nodes] hyperplane slot (index into w/idx rows) or -1 at leaves
     int32_t *d_ext_len = nullptr;      // [nodes] number of hyperplane terms (0 at leaves)
     double *d_ext_wabs = nullptr;      // [internal_slots] sum |w_i| of the slot (rounding bound of the wide kernel)
+    double *d_ext_wnorm = nullptr;     // [internal_slots] ||w||_2 of the slot, inflated (f32 fast-path bound)
+    void *d_ext_wide_nodes = nullptr;  // [nodes] ifb::WideNode records (wide kernel: one load per visit)
+    int32_t *d_ext_tree_slot = nullptr;  // [T] weight slot of each tree's root (-1 if the root is a leaf)
     int64_t *d_ext_tree_node = nullptr;  // [T+1]
     bool ext_dense_identity = false;
     int64_t ext_internal_slots = 0;

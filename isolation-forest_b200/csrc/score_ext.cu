@@ -157,7 +157,8 @@ struct ScoreExtDenseParams {
     float *path_sum;
     int32_t *depth_sum;
     int32_t k;            // real hyperplane width (<= D)
-    int32_t w_safe;       // every weight is a normal float with 2^-60 <= |w| <= 2^40
+    int32_t fast_ok;      // weights are finite with |w| <= 2^40 and the fast path is not disabled
+    double fast_scale;    // dev knob: multiplies the bound (0 = never fall back, huge = always)
     uint32_t two29;       // 0x20000000, passed at run time so the multiply below stays an IMAD (FMA pipe)
     uint64_t bias64;      // 0x38000000 << 32
 };
@@ -212,18 +213,23 @@ __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseP
         const int64_t row = tile * R + tid;
         const bool live = row < p.n_rows;
         float xr[D];
-        bool x_safe = true;   // every real feature is finite with 2^-60 <= |x| <= 2^60 (so 2^-120 <= |w*x| <= 2^100)
 #pragma unroll
         for (int c = 0; c < D; c++) {
             float v = 0.f;
             if (live && c < p.d)
                 v = p.layout == IFB_COL_MAJOR ? __ldg(p.X + (int64_t)c * p.ld + row) : __ldg(p.X + row * p.ld + c);
             xr[c] = v;
-            const uint32_t e = (__float_as_uint(v) >> 23) & 0xFFu;
-            if (c < p.d && live) x_safe = x_safe && (e - 67u <= 120u);
         }
-        // warp-uniform: the integer widening is only used when it is exact for every lane of the warp
-        const bool fast = p.w_safe && p.k == D && __all_sync(0xffffffffu, x_safe);
+        // per-row prefactor of the fast-path bound; rows with non-finite or huge features never take the fast path
+        double xsq = 0.0;
+        bool x_ok = true;
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+            xsq += (double)xr[c] * (double)xr[c];
+            x_ok = x_ok && (fabsf(xr[c]) <= 0x1p60f);
+        }
+        const double ebound = ((double)(D + 5) * 0x1.0p-24 * 1.001) * (sqrt(xsq) * 1.0000001) + (double)D * 0x1.0p-140;
+        const bool fast = x_ok && p.fast_ok && (ebound == ebound);
         float s = (p.accumulate_only && live) ? p.path_sum[row] : 0.f;
         int32_t dsum = (p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
         for (int t = 0; t < T; t++, j++) {
@@ -237,37 +243,56 @@ __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseP
             const int32_t *slot = child + npad;
             const float *leaf = reinterpret_cast<const float *>(slot + npad);
             const double *off = reinterpret_cast<const double *>(leaf + npad);
-            const float *w = reinterpret_cast<const float *>(off + ipad);
+            const double *wn = off + ipad;
+            const float *w = reinterpret_cast<const float *>(wn + ipad);
             int node = 0;
             int c = child[0];
             while (c >= 0) {
                 const int hs = slot[node];
                 const float4 *wp = reinterpret_cast<const float4 *>(w + (size_t)hs * WS);
-                double sum = 0.0;
+                // Fast decision: f32 FMA dot product (four partial chains).  For ANY evaluation order of an f32 FMA
+                // dot product |S_f - sum w_i x_i| <= gamma_k * B  (B = sum|w_i x_i|, gamma_k = k u/(1-k u),
+                // u = 2^-24), and the reference value S_ref (f32-rounded products, f64 sequential sum) satisfies
+                // |S_ref - sum w_i x_i| <= (u + k 2^-53)(1+u) B; with B <= ||w||_2 ||x||_2 (Cauchy-Schwarz):
+                //     |S_f - S_ref| <= (k + 2) * 2^-24 * 1.001 * ||w||_2 * ||x||_2 + k * 2^-148 =: E.
+                // If |S_f - offset| > E the strict test has the same outcome as the reference's; otherwise (a near
+                // tie, ~1e-5 of the visits, or non-finite / out-of-range data: `fast` is then false) the visit is
+                // evaluated with the reference's exact arithmetic below.  Decisions are therefore bit-exact.
+                bool decided = false, left = false;
                 if (fast) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                     for (int q = 0; q < D / 4; q++) {
                         const float4 w4 = wp[q];
-                        // same values, same order; NI of the 4 terms of a quad are widened on the ALU/FMA pipes
-                        const float p0 = __fmul_rn(w4.x, xr[4 * q + 0]), p1 = __fmul_rn(w4.y, xr[4 * q + 1]);
-                        const float p2 = __fmul_rn(w4.z, xr[4 * q + 2]), p3 = __fmul_rn(w4.w, xr[4 * q + 3]);
-                        sum = __dadd_rn(sum, NI >= 4 ? widen_int(p0, two29, bias64) : (double)p0);
-                        sum = __dadd_rn(sum, NI >= 1 ? widen_int(p1, two29, bias64) : (double)p1);
-                        sum = __dadd_rn(sum, NI >= 3 ? widen_int(p2, two29, bias64) : (double)p2);
-                        sum = __dadd_rn(sum, NI >= 2 ? widen_int(p3, two29, bias64) : (double)p3);
+                        s0 = fmaf(w4.x, xr[4 * q + 0], s0);
+                        s1 = fmaf(w4.y, xr[4 * q + 1], s1);
+                        s2 = fmaf(w4.z, xr[4 * q + 2], s2);
+                        s3 = fmaf(w4.w, xr[4 * q + 3], s3);
                     }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < D / 4; q++) {
-                        const float4 w4 = wp[q];
-                        // Float * Float -> Float (one rounding, no FMA), then += in Double, ascending index
-                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.x, xr[4 * q + 0]));
-                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.y, xr[4 * q + 1]));
-                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.z, xr[4 * q + 2]));
-                        sum = __dadd_rn(sum, (double)__fmul_rn(w4.w, xr[4 * q + 3]));
+                    const float sf = (s0 + s1) + (s2 + s3);
+                    const double dlt = (double)sf - off[hs];
+                    const double E = ebound * wn[hs] * p.fast_scale;        // ebound = (k+5) 2^-24 1.001 ||x||_2 + slack (per row)
+                    if (fabs(dlt) > E) {
+                        decided = true;
+                        left = dlt < 0.0;
                     }
                 }
-                node = c + ((sum < off[hs]) ? 0 : 1);
+                if (!__all_sync(__activemask(), decided)) {
+                    if (!decided) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int q = 0; q < D / 4; q++) {
+                            const float4 w4 = wp[q];
+                            // Float * Float -> Float (one rounding, no FMA), then += in Double, ascending index
+                            sum = __dadd_rn(sum, (double)__fmul_rn(w4.x, xr[4 * q + 0]));
+                            sum = __dadd_rn(sum, (double)__fmul_rn(w4.y, xr[4 * q + 1]));
+                            sum = __dadd_rn(sum, (double)__fmul_rn(w4.z, xr[4 * q + 2]));
+                            sum = __dadd_rn(sum, (double)__fmul_rn(w4.w, xr[4 * q + 3]));
+                        }
+                        left = sum < off[hs];
+                    }
+                }
+                node = c + (left ? 0 : 1);
                 c = child[node];
                 dsum++;
             }
@@ -319,16 +344,17 @@ int launch_dense(const ifb_forest *f, const ScoreExtDenseParams &p, cudaStream_t
 
 // ---- wide kernel: fully extended forests with k = d > 64 (BASELINE config 5: d = 1024) -------------------
 // A warp owns G rows of the CTA's row tile (rows live in shared memory, [row][d+4] floats).  Per tree and level
-// the warp groups its rows by current node; per group it streams the node's weight row once (coalesced LDG.128)
-// and every lane accumulates, for each row of the group, the f64 sum of ITS terms (i = 128j + 4*lane + q, the
-// f32 products rounded exactly as the reference's).  The 32 partial sums are combined by a fixed shuffle tree.
-//
-// Exactness.  The reference adds the same f64 addends p_i = (double)fl32(w_i x_i) in index order; the tree above
-// is a re-association.  For ANY two summation orders of the same k addends  |S_a - S_b| <= 2 gamma_{k-1} sum|p_i|
-// (gamma_n = n u / (1 - n u), u = 2^-53), and  sum|p_i| <= max_i|x_i| * sum_i|w_i| * (1 + 2^-23) =: A.
-// Hence if |S - offset| > 4 k u A the strict comparison S < offset has the same outcome in the reference's order.
-// Otherwise (a near tie, or NaN/inf anywhere: A is then non-finite and the test fails) the visit is recomputed
-// in the reference's sequential order.  Decisions are therefore bit-exact; the fallback is taken ~never.
+// the warp groups its rows by current node; per group it streams the node's weight row once (coalesced LDG.128,
+// the forest is L2 resident) and the 32 lanes split the terms (i = 128 j + 4 lane + q).  Three tiers, each one
+// PROVABLY giving the reference's decision (the reference adds p_i = (double)fl32(w_i x_i) in index order):
+//   1. f32 FMA partial dots combined by a shuffle tree.  |S_1 - S_ref| <= (k+16) 2^-24 1.001 ||w||_2 ||x||_2 =: E1
+//      (Higham's bound for an FMA dot product in ANY order, plus the reference's own product roundings,
+//      Cauchy-Schwarz for sum|w_i x_i|).  |S_1 - offset| > E1  =>  same outcome as the reference.
+//   2. the exact addends p_i, summed in f64 per lane and by a shuffle tree (a re-association):
+//      |S_2 - S_ref| <= 2 gamma_{k-1} sum|p_i| <= 4 k 2^-53 max|x| sum|w| =: E2.   |S_2 - offset| > E2 => same.
+//   3. the reference's sequential order.
+// Tier 2 is reached by ~1e-3 of the visits at k = 1024, tier 3 essentially never; rows with non-finite or huge
+// features skip tier 1 (its bound would not hold) and fall through.
 struct ScoreExtWideParams {
     const float *X;
     int64_t n_rows, ld;
@@ -336,13 +362,15 @@ struct ScoreExtWideParams {
     const float *w;
     const double *off;
     const double *wabs;
-    const float *leaf;
-    const int32_t *child, *hp;
+    const WideNode *nodes;
+    const int32_t *tree_slot;
     const int64_t *tree_node;
     int32_t num_trees, total_trees;
     int32_t rows_per_tile;   // multiple of the warp count
     float avg_path;
     int32_t accumulate_only;
+    int32_t fast_ok;
+    double fast_scale;
     double *scores;
     float *path_sum;
     int32_t *depth_sum;
@@ -355,10 +383,12 @@ __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtW
     const int R = G * NW;
     const int d = p.d;
     const int xstride = d + 4;  // floats; keeps 16-byte alignment, breaks the power-of-two row pitch
-    float *rowmax = xs_w + (size_t)R * xstride;  // [R] max |x| per row
+    float *rowmax = xs_w + (size_t)R * xstride;                         // [R] max |x| per row (NaN if non-finite)
+    double *rownorm = reinterpret_cast<double *>(rowmax + ((R + 1) & ~1));  // [R] ||x||_2, inflated
     const int64_t n_tiles = (p.n_rows + R - 1) / R;
     const int chunks = d / 128;        // full 128-term chunks (4 terms per lane)
     const int tail0 = chunks * 128;    // remaining terms [tail0, d) handled 1 per lane per step
+    constexpr int PB = 8;              // weight chunks in flight per warp
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * R;
         __syncthreads();
@@ -376,38 +406,49 @@ __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtW
             }
         }
         __syncthreads();
-        // per-row max |x| (NaN/inf propagate into the bound and force the sequential path)
         for (int g = 0; g < G; g++) {
             const int r = warp * G + g;
             float m = 0.f;
+            double sq = 0.0;
             bool bad = false;
             for (int c = lane; c < d; c += 32) {
-                const float v = fabsf(xs_w[(size_t)r * xstride + c]);
+                const float xv = xs_w[(size_t)r * xstride + c];
+                const float v = fabsf(xv);
                 bad = bad || !(v <= 3.0e38f);
                 m = fmaxf(m, v);
+                sq += (double)xv * (double)xv;
             }
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            for (int o = 16; o > 0; o >>= 1) {
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            }
             bad = __any_sync(0xffffffffu, bad);
-            if (lane == 0) rowmax[r] = bad ? __int_as_float(0x7fc00000) : m;
+            if (lane == 0) {
+                rowmax[r] = bad ? __int_as_float(0x7fc00000) : m;
+                rownorm[r] = sqrt(sq) * 1.000001;
+            }
         }
         __syncwarp();
 
         float s[G];
         int32_t dsum[G];
+        bool tier1[G];   // warp-uniform: this row may use the f32 tier
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const int64_t row = row0 + warp * G + g;
             const bool live = row < p.n_rows;
             s[g] = (p.accumulate_only && live) ? p.path_sum[row] : 0.f;
             dsum[g] = (p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
+            tier1[g] = p.fast_ok && (rowmax[warp * G + g] <= 0x1p60f);
         }
         for (int t = 0; t < p.num_trees; t++) {
             const int64_t base = p.tree_node[t];
-            int32_t node[G], ch[G];      // warp-uniform
+            int32_t node[G], ch[G];      // warp-uniform: current node and ITS weight slot (-1 = leaf)
+            const int32_t root_slot = __ldg(p.tree_slot + t);
 #pragma unroll
             for (int g = 0; g < G; g++) {
                 node[g] = 0;
-                ch[g] = __ldg(p.child + base);
+                ch[g] = root_slot;
             }
             while (true) {
                 uint32_t pending = 0;    // rows still at an internal node
@@ -423,77 +464,133 @@ __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtW
 #pragma unroll
                     for (int g = 0; g < G; g++) if (((pending >> g) & 1u) && node[g] == n0) grp |= 1u << g;
                     pending &= ~grp;
-                    const int64_t gn = base + n0;
-                    const int32_t slot = __ldg(p.hp + gn);
+                    int32_t slot = 0;
+#pragma unroll
+                    for (int g = 0; g < G; g++) if (g == g0) slot = ch[g];
+                    // the node record and the weight row are independent loads: one L2 round trip per visit
                     const float *wrow = p.w + (int64_t)slot * d;
-                    // four independent f64 chains per (lane, row): the order is already covered by the bound below
-                    double acc[G][4];
+                    const int4 *nrec = reinterpret_cast<const int4 *>(p.nodes + (base + n0));
+                    const int4 na = __ldg(nrec), nb = __ldg(nrec + 1);
+                    const double offv = __hiloint2double(na.y, na.x);
+                    const float wnorm_f = __int_as_float(na.z);
+                    const int32_t cbase = nb.x, slot_l = nb.y, slot_r = nb.z;
+                    uint32_t todo = grp;                         // rows whose decision is still open
+                    uint32_t leftmask = 0;
+
+                    // ---- tier 1: f32 FMA ----
+                    uint32_t g1 = 0;
 #pragma unroll
-                    for (int g = 0; g < G; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.0;
-                    // weight chunks are fetched PB at a time (independent 512-byte coalesced loads in flight per
-                    // warp) before any arithmetic touches them: the forest lives in L2, not in shared memory
-                    constexpr int PB = 8;
-                    for (int jb = 0; jb < chunks; jb += PB) {
-                        float4 wv[PB];
+                    for (int g = 0; g < G; g++) if (((grp >> g) & 1u) && tier1[g]) g1 |= 1u << g;
+                    const double e1_node = ((double)(d + 16) * 0x1.0p-24 * 1.001) * (double)wnorm_f * p.fast_scale;
+                    if (g1) {
+                        float a32[G][4];
 #pragma unroll
-                        for (int u = 0; u < PB; u++)
-                            if (jb + u < chunks)
-                                wv[u] = __ldg(reinterpret_cast<const float4 *>(wrow + (jb + u) * 128) + lane);
+                        for (int g = 0; g < G; g++) a32[g][0] = a32[g][1] = a32[g][2] = a32[g][3] = 0.f;
+                        for (int jb = 0; jb < chunks; jb += PB) {
+                            float4 wv[PB];
 #pragma unroll
-                        for (int u = 0; u < PB; u++) {
-                            if (jb + u < chunks) {
-                                const float4 w4 = wv[u];
+                            for (int u = 0; u < PB; u++)
+                                if (jb + u < chunks) wv[u] = __ldg(reinterpret_cast<const float4 *>(wrow + (jb + u) * 128) + lane);
 #pragma unroll
-                                for (int g = 0; g < G; g++) {
-                                    if ((grp >> g) & 1u) {
-                                        const float4 x4 = *reinterpret_cast<const float4 *>(
-                                            xs_w + (size_t)(warp * G + g) * xstride + (jb + u) * 128 + lane * 4);
-                                        acc[g][0] = __dadd_rn(acc[g][0], (double)__fmul_rn(w4.x, x4.x));
-                                        acc[g][1] = __dadd_rn(acc[g][1], (double)__fmul_rn(w4.y, x4.y));
-                                        acc[g][2] = __dadd_rn(acc[g][2], (double)__fmul_rn(w4.z, x4.z));
-                                        acc[g][3] = __dadd_rn(acc[g][3], (double)__fmul_rn(w4.w, x4.w));
+                            for (int u = 0; u < PB; u++) {
+                                if (jb + u < chunks) {
+#pragma unroll
+                                    for (int g = 0; g < G; g++) {
+                                        if ((g1 >> g) & 1u) {
+                                            const float4 x4 = *reinterpret_cast<const float4 *>(
+                                                xs_w + (size_t)(warp * G + g) * xstride + (jb + u) * 128 + lane * 4);
+                                            a32[g][0] = fmaf(wv[u].x, x4.x, a32[g][0]);
+                                            a32[g][1] = fmaf(wv[u].y, x4.y, a32[g][1]);
+                                            a32[g][2] = fmaf(wv[u].z, x4.z, a32[g][2]);
+                                            a32[g][3] = fmaf(wv[u].w, x4.w, a32[g][3]);
+                                        }
                                     }
                                 }
                             }
                         }
-                    }
-                    for (int i = tail0 + lane; i < d; i += 32) {
-                        const float wv = __ldg(wrow + i);
+                        for (int i = tail0 + lane; i < d; i += 32) {
+                            const float wv1 = __ldg(wrow + i);
 #pragma unroll
-                        for (int g = 0; g < G; g++)
-                            if ((grp >> g) & 1u)
-                                acc[g][0] = __dadd_rn(acc[g][0], (double)__fmul_rn(wv, xs_w[(size_t)(warp * G + g) * xstride + i]));
+                            for (int g = 0; g < G; g++)
+                                if ((g1 >> g) & 1u) a32[g][0] = fmaf(wv1, xs_w[(size_t)(warp * G + g) * xstride + i], a32[g][0]);
+                        }
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            if ((g1 >> g) & 1u) {
+                                float v = (a32[g][0] + a32[g][1]) + (a32[g][2] + a32[g][3]);
+                                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                                v = __shfl_sync(0xffffffffu, v, 0);
+                                const double E1 = e1_node * rownorm[warp * G + g] + (double)d * 0x1.0p-140;
+                                const double dlt = (double)v - offv;
+                                if (fabs(dlt) > E1) {
+                                    todo &= ~(1u << g);
+                                    if (dlt < 0.0) leftmask |= 1u << g;
+                                }
+                            }
+                        }
                     }
-                    const double offv = __ldg(p.off + gn);
-                    const double wabs = __ldg(p.wabs + slot);
-                    const int32_t cbase = __ldg(p.child + gn);   // left child of n0 (same for the whole group)
+                    // ---- tier 2: exact addends, f64, lane-parallel ----
+                    if (todo) {
+                        double acc[G][4];
+#pragma unroll
+                        for (int g = 0; g < G; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.0;
+                        for (int j = 0; j < chunks; j++) {
+                            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wrow + j * 128) + lane);
+#pragma unroll
+                            for (int g = 0; g < G; g++) {
+                                if ((todo >> g) & 1u) {
+                                    const float4 x4 = *reinterpret_cast<const float4 *>(
+                                        xs_w + (size_t)(warp * G + g) * xstride + j * 128 + lane * 4);
+                                    acc[g][0] = __dadd_rn(acc[g][0], (double)__fmul_rn(w4.x, x4.x));
+                                    acc[g][1] = __dadd_rn(acc[g][1], (double)__fmul_rn(w4.y, x4.y));
+                                    acc[g][2] = __dadd_rn(acc[g][2], (double)__fmul_rn(w4.z, x4.z));
+                                    acc[g][3] = __dadd_rn(acc[g][3], (double)__fmul_rn(w4.w, x4.w));
+                                }
+                            }
+                        }
+                        for (int i = tail0 + lane; i < d; i += 32) {
+                            const float wv1 = __ldg(wrow + i);
+#pragma unroll
+                            for (int g = 0; g < G; g++)
+                                if ((todo >> g) & 1u)
+                                    acc[g][0] = __dadd_rn(acc[g][0], (double)__fmul_rn(wv1, xs_w[(size_t)(warp * G + g) * xstride + i]));
+                        }
+                        const double wabs = __ldg(p.wabs + slot);
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            if ((todo >> g) & 1u) {
+                                double v = __dadd_rn(__dadd_rn(acc[g][0], acc[g][1]), __dadd_rn(acc[g][2], acc[g][3]));
+                                for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+                                v = __shfl_sync(0xffffffffu, v, 0);
+                                const double A = (double)rowmax[warp * G + g] * wabs * 1.0000002;
+                                const double E2 = 4.0 * (double)d * 0x1.0p-53 * A;
+                                bool left;
+                                if (fabs(v - offv) > E2) {
+                                    left = v < offv;
+                                } else {
+                                    // ---- tier 3: the reference's sequential order, every lane redundantly ----
+                                    double sq = 0.0;
+                                    const float *xr = xs_w + (size_t)(warp * G + g) * xstride;
+                                    for (int i = 0; i < d; i++) sq = __dadd_rn(sq, (double)__fmul_rn(__ldg(wrow + i), xr[i]));
+                                    left = sq < offv;
+                                }
+                                if (left) leftmask |= 1u << g;
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         if ((grp >> g) & 1u) {
-                            double v = __dadd_rn(__dadd_rn(acc[g][0], acc[g][1]), __dadd_rn(acc[g][2], acc[g][3]));
-                            for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
-                            v = __shfl_sync(0xffffffffu, v, 0);
-                            const double A = (double)rowmax[warp * G + g] * wabs * 1.0000002;
-                            const double tol = 4.0 * (double)d * 0x1.0p-53 * A;
-                            bool left;
-                            if (fabs(v - offv) > tol) {
-                                left = v < offv;
-                            } else {
-                                // near tie or non-finite data: the reference's sequential order, every lane redundantly
-                                double sq = 0.0;
-                                const float *xr = xs_w + (size_t)(warp * G + g) * xstride;
-                                for (int i = 0; i < d; i++) sq = __dadd_rn(sq, (double)__fmul_rn(__ldg(wrow + i), xr[i]));
-                                left = sq < offv;
-                            }
-                            node[g] = cbase + (left ? 0 : 1);
-                            ch[g] = __ldg(p.child + base + node[g]);
+                            const bool l = (leftmask >> g) & 1u;
+                            node[g] = cbase + (l ? 0 : 1);
+                            ch[g] = l ? slot_l : slot_r;
                             dsum[g]++;
                         }
                     }
                 }
             }
 #pragma unroll
-            for (int g = 0; g < G; g++) s[g] = s[g] + __ldg(p.leaf + base + node[g]);
+            for (int g = 0; g < G; g++) s[g] = s[g] + __ldg(&p.nodes[base + node[g]].leaf);
         }
         if (lane == 0) {
 #pragma unroll
@@ -518,7 +615,7 @@ int launch_wide(const ifb_forest *f, const ScoreExtWideParams &p0, cudaStream_t 
     constexpr int NW = 16;
     ScoreExtWideParams p = p0;
     p.rows_per_tile = G * NW;
-    const size_t smem = ((size_t)G * NW * (p.d + 4) + (size_t)G * NW) * 4;
+    const size_t smem = ((size_t)G * NW * (p.d + 4) + (size_t)((G * NW + 1) & ~1)) * 4 + (size_t)G * NW * 8;
     const int sms = device_sm_count(f->device);
     const int64_t n_tiles = (p.n_rows + G * NW - 1) / (G * NW);
     const int grid = (int)std::min<int64_t>(n_tiles, sms);
@@ -544,7 +641,8 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
         q.num_trees = f->num_trees; q.total_trees = f->num_trees; q.blob_max = f->ext_blob_max;
         q.avg_path = f->avg_path_norm; q.accumulate_only = accumulate_only ? 1 : 0;
         q.scores = scores; q.path_sum = path_sum; q.depth_sum = depth_sum;
-        q.k = f->max_nnz; q.w_safe = (f->ext_w_safe && getenv("IFB_EXT_NOSPLIT") == nullptr) ? 1 : 0; q.two29 = 0x20000000u; q.bias64 = 0x3800000000000000ull;
+        q.k = f->max_nnz; q.fast_ok = (f->ext_w_safe && getenv("IFB_EXT_NOFAST") == nullptr) ? 1 : 0;
+        q.fast_scale = getenv("IFB_EXT_FAST_SCALE") ? atof(getenv("IFB_EXT_FAST_SCALE")) : 1.0; q.two29 = 0x20000000u; q.bias64 = 0x3800000000000000ull;
         int rc;
         switch (f->ext_blob_D) {
             case 8: rc = launch_dense<8>(f, q, stream); break;
@@ -557,14 +655,17 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
     if (f->ext_dense_identity && f->max_nnz == d && d > 64 && d % 4 == 0 && getenv("IFB_EXT_GENERIC") == nullptr) {
         ScoreExtWideParams q;
         q.X = X; q.n_rows = n_rows; q.ld = ld; q.d = d; q.layout = layout;
-        q.w = f->d_ext_w; q.off = f->d_ext_off; q.wabs = f->d_ext_wabs; q.leaf = f->d_ext_leaf;
-        q.child = f->d_ext_child; q.hp = f->d_ext_hp; q.tree_node = f->d_ext_tree_node;
+        q.w = f->d_ext_w; q.off = f->d_ext_off; q.wabs = f->d_ext_wabs;
+        q.nodes = reinterpret_cast<const WideNode *>(f->d_ext_wide_nodes); q.tree_slot = f->d_ext_tree_slot;
+        q.fast_ok = (f->ext_w_safe && getenv("IFB_EXT_NOFAST") == nullptr) ? 1 : 0;
+        q.fast_scale = getenv("IFB_EXT_FAST_SCALE") ? atof(getenv("IFB_EXT_FAST_SCALE")) : 1.0;
+        q.tree_node = f->d_ext_tree_node;
         q.num_trees = f->num_trees; q.total_trees = f->num_trees; q.rows_per_tile = 0;
         q.avg_path = f->avg_path_norm; q.accumulate_only = accumulate_only ? 1 : 0;
         q.scores = scores; q.path_sum = path_sum; q.depth_sum = depth_sum;
         // rows per warp: as many as shared memory allows (<= 4), 16 warps per CTA
         const size_t budget = (size_t)device_smem_optin(f->device) - 1024;
-        int G = (int)std::min<size_t>(4, budget / ((size_t)16 * ((size_t)d + 5) * 4));
+        int G = (int)std::min<size_t>(4, budget / ((size_t)16 * ((size_t)d + 8) * 4));
         if (G >= 1) {
             switch (G) {
                 case 4: return launch_wide<4>(f, q, stream);

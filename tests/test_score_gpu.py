@@ -399,3 +399,41 @@ def test_fused_scatter_emulated_ranks(nat, oracle, dev, world, T, d):
     e = acc / np.float32(T)
     z = (-e / oracle.avg_path_length(256)).astype(np.float64)
     assert np.max(np.abs(got - np.power(2.0, z)) / got) <= 1e-12
+
+
+@pytest.mark.parametrize("d", [16, 64, 6, 128, 260])
+def test_extended_exact_ties_are_decided_like_the_reference(nat, oracle, dev, d, monkeypatch):
+    """The dense extended kernel decides most visits from an f32 FMA dot product guarded by a rounding bound and
+    re-evaluates near ties with the reference's arithmetic.  Hand-built trees put the offset exactly ON the
+    reference's sequential value for a row, and one f64 ulp on either side of it."""
+    rng = np.random.default_rng(5 + d)
+    n = 96
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    trees = []
+    for r in range(n):
+        w = rng.standard_normal(d)
+        w = (w / np.linalg.norm(w)).astype(np.float32)
+        prod = (w * X[r]).astype(np.float32).astype(np.float64)      # f32 products (one rounding each)
+        sref = np.cumsum(prod)[-1]                                   # sequential f64 sum, ascending index
+        for off in (sref, np.nextafter(sref, np.inf), np.nextafter(sref, -np.inf)):
+            trees.append((w, off))
+    T = len(trees)
+    tables = dict(extended=True, num_trees=T, num_samples=256, total_num_features=d,
+                  node_off=np.arange(0, 3 * T + 1, 3, dtype=np.int32), left=np.tile([1, -1, -1], T).astype(np.int32),
+                  right=np.tile([2, -1, -1], T).astype(np.int32),
+                  num_instances=np.tile([-1, 3, 200], T).astype(np.int64),      # the two leaves are distinguishable
+                  offset=np.concatenate([[o, 0.0, 0.0] for _, o in trees]),
+                  hp_off=np.concatenate([[0], np.cumsum(np.tile([d, 0, 0], T))]).astype(np.int64),
+                  hp_idx=np.tile(np.arange(d, dtype=np.int32), T), hp_w=np.concatenate([w for w, _ in trees]))
+    F = nat.NativeForest.from_tables(tables)
+    ref = oracle.Forest(tables).score(X, threads=4, want_parts=True)
+    # sanity of the construction: row r goes right / left / right in its own three trees
+    one = oracle.Forest(tables)
+    for r in (0, 17, 95):
+        got = [one.path_length(3 * r + j, X[r]) for j in range(3)]
+        assert got[0] == got[2] != got[1]
+    assert_parity(F.score_device(colmajor_cuda(X), want_parts=True), ref)
+    # the same through the always-exact path (bound scaled up so that every visit falls back)
+    monkeypatch.setenv("IFB_EXT_FAST_SCALE", "1e30")
+    F2 = nat.NativeForest.from_tables(tables)
+    assert_parity(F2.score_device(colmajor_cuda(X), want_parts=True), ref)
