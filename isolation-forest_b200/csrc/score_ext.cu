@@ -376,7 +376,7 @@ struct ScoreExtWideParams {
     int32_t *depth_sum;
 };
 
-template <int G, int NW>
+template <int G, int NW, int PB>
 __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtWideParams p) {
     extern __shared__ __align__(16) float xs_w[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtW
     const int64_t n_tiles = (p.n_rows + R - 1) / R;
     const int chunks = d / 128;        // full 128-term chunks (4 terms per lane)
     const int tail0 = chunks * 128;    // remaining terms [tail0, d) handled 1 per lane per step
-    constexpr int PB = 8;              // weight chunks in flight per warp
+    // PB = weight chunks in flight per warp
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * R;
         __syncthreads();
@@ -610,17 +610,16 @@ __global__ void __launch_bounds__(NW * 32) score_ext_wide_kernel(const ScoreExtW
     }
 }
 
-template <int G>
+template <int G, int NW, int PB>
 int launch_wide(const ifb_forest *f, const ScoreExtWideParams &p0, cudaStream_t stream) {
-    constexpr int NW = 16;
     ScoreExtWideParams p = p0;
     p.rows_per_tile = G * NW;
     const size_t smem = ((size_t)G * NW * (p.d + 4) + (size_t)((G * NW + 1) & ~1)) * 4 + (size_t)G * NW * 8;
     const int sms = device_sm_count(f->device);
     const int64_t n_tiles = (p.n_rows + G * NW - 1) / (G * NW);
     const int grid = (int)std::min<int64_t>(n_tiles, sms);
-    IFB_CUDA(cudaFuncSetAttribute(score_ext_wide_kernel<G, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    score_ext_wide_kernel<G, NW><<<grid, NW * 32, smem, stream>>>(p);
+    IFB_CUDA(cudaFuncSetAttribute(score_ext_wide_kernel<G, NW, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    score_ext_wide_kernel<G, NW, PB><<<grid, NW * 32, smem, stream>>>(p);
     IFB_CUDA(cudaGetLastError());
     count_launch();
     return IFB_OK;
@@ -666,12 +665,17 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
         // rows per warp: as many as shared memory allows (<= 4), 16 warps per CTA
         const size_t budget = (size_t)device_smem_optin(f->device) - 1024;
         int G = (int)std::min<size_t>(4, budget / ((size_t)16 * ((size_t)d + 8) * 4));
+        static const int wide_nw = getenv("IFB_WIDE_NW") ? atoi(getenv("IFB_WIDE_NW")) : 32;
+        if (wide_nw == 32 && budget / ((size_t)32 * ((size_t)d + 8) * 4) >= 1) {
+            if (budget / ((size_t)32 * ((size_t)d + 8) * 4) >= 2 && getenv("IFB_WIDE_G1") == nullptr) return launch_wide<2, 32, 4>(f, q, stream);
+            return launch_wide<1, 32, 4>(f, q, stream);
+        }
         if (G >= 1) {
             switch (G) {
-                case 4: return launch_wide<4>(f, q, stream);
-                case 3: return launch_wide<3>(f, q, stream);
-                case 2: return launch_wide<2>(f, q, stream);
-                default: return launch_wide<1>(f, q, stream);
+                case 4: return launch_wide<4, 16, 8>(f, q, stream);
+                case 3: return launch_wide<3, 16, 8>(f, q, stream);
+                case 2: return launch_wide<2, 16, 8>(f, q, stream);
+                default: return launch_wide<1, 16, 8>(f, q, stream);
             }
         }
     }
