@@ -164,6 +164,14 @@ IFB_API int ifb_score_scatter_device(const ifb_forest *forest, const float *X, i
                                      float *const *peer_partials /*[world]*/, void *stream);
 IFB_API int ifb_finalize_gathered_device(int32_t device, const float *partials, int32_t world, int64_t rows_local,
                                          int32_t total_num_trees, int32_t num_samples, double *scores, void *stream);
+/* Device-side barrier for the fused layout (no collective library involved): every rank owns `world` 32-bit
+ * flags in peer-visible memory.  ifb_peer_signal_device (enqueued after the scatter kernel) stores `epoch` into
+ * slot [rank] of every peer's flag array with system scope; ifb_peer_wait_device (enqueued before the gathered
+ * finalize) spins until all `world` local slots hold `epoch`.  Epochs must increase from call to call. */
+IFB_API int ifb_peer_signal_device(int32_t device, int32_t world, int32_t rank, uint32_t *const *peer_flags /*[world]*/,
+                                   uint32_t epoch, void *stream);
+IFB_API int ifb_peer_wait_device(int32_t device, int32_t world, const uint32_t *local_flags, uint32_t epoch,
+                                 void *stream);
 
 /* prediction column: (score >= threshold) ? 1.0 : 0.0, all 0.0 when threshold <= 0
  * (IF/IsolationForestModel.scala:143-148). */

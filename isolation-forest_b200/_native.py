@@ -74,6 +74,8 @@ SYMBOLS = {
                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ifb_finalize_gathered_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                                C.c_void_p, C.c_void_p]),
+    "ifb_peer_signal_device": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "ifb_peer_wait_device": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_uint32, C.c_void_p]),
     "ifb_predict_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
     "ifb_fit_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                  C.POINTER(FitParams), C.POINTER(C.c_void_p), C.c_void_p]),

@@ -193,6 +193,18 @@ int ifb_finalize_gathered_device(int32_t device, const float *partials, int32_t 
                                     (cudaStream_t)stream);
 }
 
+int ifb_peer_signal_device(int32_t device, int32_t world, int32_t rank, uint32_t *const *peer_flags, uint32_t epoch,
+                           void *stream) {
+    IFB_REQUIRE(world >= 1 && world <= kMaxScatterRanks && rank >= 0 && rank < world && peer_flags, "bad arguments");
+    DeviceGuard dg(device);
+    return launch_peer_signal(world, rank, peer_flags, epoch, (cudaStream_t)stream);
+}
+int ifb_peer_wait_device(int32_t device, int32_t world, const uint32_t *local_flags, uint32_t epoch, void *stream) {
+    IFB_REQUIRE(world >= 1 && world <= kMaxScatterRanks && local_flags, "bad arguments");
+    DeviceGuard dg(device);
+    return launch_peer_wait(world, local_flags, epoch, (cudaStream_t)stream);
+}
+
 int ifb_predict_device(int32_t device, const double *scores, int64_t n_rows, double threshold, double *labels,
                        void *stream) {
     IFB_REQUIRE(n_rows == 0 || (scores && labels), "null buffer");

@@ -33,6 +33,33 @@ __global__ void finalize_gathered_kernel(const float *__restrict__ partials, int
     }
 }
 
+// ---- device-side barrier over peer memory (fused tree-sharded layout) ----
+struct PeerFlags {
+    uint32_t *p[kMaxScatterRanks];
+};
+__global__ void peer_signal_kernel(PeerFlags f, int world, int rank, uint32_t epoch) {
+    // launched after the scatter kernel on the same stream: its peer stores are complete; publish the epoch
+    const int o = threadIdx.x;
+    if (o < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[o] + rank), "r"(epoch) : "memory");
+    }
+}
+__global__ void peer_wait_kernel(const uint32_t *flags, int world, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        uint32_t v = 0;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (true) {   // bounded to 30 s: a lost peer must surface as an error, not hang the GPU
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+            if ((int32_t)(v - epoch) >= 0) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 30000000000ull) __trap();
+        }
+    }
+}
+
 // IF/IsolationForestModel.scala:143-148
 __global__ void predict_kernel(const double *__restrict__ scores, int64_t n, double thr, double *__restrict__ labels) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -136,6 +163,21 @@ int launch_finalize_gathered(const float *partials, int32_t world, int64_t rows_
     if (rows_local == 0) return IFB_OK;
     const int grid = (int)std::min<int64_t>((rows_local + 255) / 256, 148 * 16);
     finalize_gathered_kernel<<<grid, 256, 0, stream>>>(partials, world, rows_local, (float)total_trees, avg_path, scores);
+    IFB_CUDA(cudaGetLastError());
+    count_launch();
+    return IFB_OK;
+}
+
+int launch_peer_signal(int world, int rank, uint32_t *const *peer_flags, uint32_t epoch, cudaStream_t stream) {
+    PeerFlags f;
+    for (int i = 0; i < kMaxScatterRanks; i++) f.p[i] = i < world ? peer_flags[i] : nullptr;
+    peer_signal_kernel<<<1, 32, 0, stream>>>(f, world, rank, epoch);
+    IFB_CUDA(cudaGetLastError());
+    count_launch();
+    return IFB_OK;
+}
+int launch_peer_wait(int world, const uint32_t *local_flags, uint32_t epoch, cudaStream_t stream) {
+    peer_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, epoch);
     IFB_CUDA(cudaGetLastError());
     count_launch();
     return IFB_OK;

@@ -201,6 +201,8 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
 int launch_finalize(const float *path_sum, int64_t n_rows, int32_t total_trees, float avg_path, double *scores,
                     cudaStream_t stream);
 int launch_predict(const double *scores, int64_t n_rows, double threshold, double *labels, cudaStream_t stream);
+int launch_peer_signal(int world, int rank, uint32_t *const *peer_flags, uint32_t epoch, cudaStream_t stream);
+int launch_peer_wait(int world, const uint32_t *local_flags, uint32_t epoch, cudaStream_t stream);
 int launch_finalize_gathered(const float *partials, int32_t world, int64_t rows_local, int32_t total_trees, float avg_path,
                              double *scores, cudaStream_t stream);
 int launch_transpose(const float *in, int64_t n, int32_t d, int64_t ld_in, float *out, int64_t ld_out,

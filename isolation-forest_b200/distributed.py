@@ -95,10 +95,15 @@ def score_tree_sharded(local_forest, X, total_num_trees: int, num_samples: int, 
 class ScatterContext:
     """Peer-memory buffers for the FUSED tree-sharded transform (include/ifb200.h: ifb_score_scatter_device).
 
-    Rank o owns rows [cut[o], cut[o+1]) and exposes a buffer of world * rows_o floats through CUDA IPC; every rank
-    maps every peer's buffer once.  A transform is then: one scoring kernel per rank whose epilogue stores each
-    row's partial path-length sum into the owner's buffer over NVLink, a barrier, and a rank-ordered sum + score
-    epilogue on the owner.  No NCCL on the data path (the barrier is a one-element collective)."""
+    Rank o owns rows [cut[o], cut[o+1]) and exposes, through CUDA IPC, TWO buffers of world * rows_o floats
+    (alternated from call to call) plus `world` 32-bit flags; every rank maps every peer's allocation once.
+    A transform is then: one scoring kernel per rank whose epilogue stores each row's partial path-length sum into
+    the owner's buffer over NVLink, a device-side flag barrier (system-scope release/acquire on the peers' flags),
+    and a rank-ordered sum + score epilogue on the owner.  No collective library on the data path.
+
+    Why two buffers: rank B may start step k+1's scatter while rank A still reads step k's partials; with the
+    buffers alternating, the next write into a buffer (step k+2) happens after every rank has passed step k+1's
+    barrier, i.e. after every rank finished reading step k."""
 
     def __init__(self, n_rows: int, group=None):
         import ctypes as C
@@ -114,54 +119,69 @@ class ScatterContext:
         self.n_rows = n_rows
         self.cuts = [row_shard(n_rows, r, self.world)[0] for r in range(self.world)] + [n_rows]
         self.rows_local = self.cuts[self.rank + 1] - self.cuts[self.rank]
+        rows = [self.cuts[o + 1] - self.cuts[o] for o in range(self.world)]
+        # allocation layout of rank o: [flags: 256 B][buffer 0: world*rows_o floats][buffer 1: same]
+        self._buf_bytes = [max(16, (self.world * r * 4 + 255) & ~255) for r in rows]
         p = C.c_void_p()
-        nat.check(nat.lib().ifb_device_alloc(self.device, max(4, self.world * self.rows_local * 4), C.byref(p)))
+        nat.check(nat.lib().ifb_device_alloc(self.device, 256 + 2 * self._buf_bytes[self.rank], C.byref(p)))
         self.local_ptr = p
+        torch.cuda.synchronize()
+        zero = torch.zeros(64, dtype=torch.int32)
+        nat.check(nat.lib().ifb_copy_to_device(self.device, p, C.c_void_p(zero.data_ptr()), 256))
         handle = C.create_string_buffer(64)
         nat.check(nat.lib().ifb_ipc_export(self.device, p, handle))
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        self.peers = []
+        self.bases = []
         for o in range(self.world):
             if o == self.rank:
-                self.peers.append(p)
+                self.bases.append(p.value)
             else:
                 q = C.c_void_p()
                 nat.check(nat.lib().ifb_ipc_open(self.device, C.create_string_buffer(handles[o], 64), C.byref(q)))
-                self.peers.append(q)
-        self._peer_arr = (C.c_void_p * self.world)(*[x.value for x in self.peers])
+                self.bases.append(q.value)
+        self._flag_arr = (C.c_void_p * self.world)(*self.bases)
+        self._peer_arr = [(C.c_void_p * self.world)(*[self.bases[o] + 256 + b * self._buf_bytes[o] for o in range(self.world)])
+                          for b in (0, 1)]
         self._cut_arr = (C.c_int64 * (self.world + 1))(*self.cuts)
+        self.epoch = 0
+        dist.barrier(group=group)   # every rank has zeroed its flags before anyone signals
 
     def score(self, local_forest, X, total_num_trees: int, num_samples: int, scores_local=None):
         """Returns this rank's slice of the scores (rows cut[rank] .. cut[rank+1])."""
         import ctypes as C
 
         import torch
-        import torch.distributed as dist
 
         nat = self.nat
         n, d, ld, layout = nat.NativeForest._layout_of(tuple(X.shape), tuple(X.stride()))
         assert n == self.n_rows and layout == nat.COL_MAJOR
+        self.epoch += 1
+        b = self.epoch & 1
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         nat.check(nat.lib().ifb_score_scatter_device(local_forest.handle, C.c_void_p(X.data_ptr()), n, d, ld, layout,
-                                                     self.world, self.rank, self._cut_arr, self._peer_arr, st))
-        dist.barrier(group=self.group)   # stream-ordered: every rank's stores have landed before anyone reads
+                                                     self.world, self.rank, self._cut_arr, self._peer_arr[b], st))
+        nat.check(nat.lib().ifb_peer_signal_device(self.device, self.world, self.rank, self._flag_arr, self.epoch, st))
+        nat.check(nat.lib().ifb_peer_wait_device(self.device, self.world, C.c_void_p(self.bases[self.rank]), self.epoch, st))
         if scores_local is None:
             scores_local = torch.empty(self.rows_local, dtype=torch.float64, device=X.device)
-        nat.check(nat.lib().ifb_finalize_gathered_device(self.device, self.local_ptr, self.world, self.rows_local,
+        local_buf = C.c_void_p(self.bases[self.rank] + 256 + b * self._buf_bytes[self.rank])
+        nat.check(nat.lib().ifb_finalize_gathered_device(self.device, local_buf, self.world, self.rows_local,
                                                          total_num_trees, num_samples,
                                                          C.c_void_p(scores_local.data_ptr()), st))
         return scores_local
 
     def close(self):
+        import ctypes as C
+
         import torch
         import torch.distributed as dist
 
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
-        for o, q in enumerate(self.peers):
+        for o, q in enumerate(self.bases):
             if o != self.rank:
-                self.nat.lib().ifb_ipc_close(self.device, q)
+                self.nat.lib().ifb_ipc_close(self.device, C.c_void_p(q))
         dist.barrier(group=self.group)
         self.nat.lib().ifb_device_free(self.device, self.local_ptr)
-        self.peers = []
+        self.bases = []

@@ -437,3 +437,22 @@ def test_extended_exact_ties_are_decided_like_the_reference(nat, oracle, dev, d,
     monkeypatch.setenv("IFB_EXT_FAST_SCALE", "1e30")
     F2 = nat.NativeForest.from_tables(tables)
     assert_parity(F2.score_device(colmajor_cuda(X), want_parts=True), ref)
+
+
+def test_peer_flag_barrier_emulated(nat, dev):
+    """ifb_peer_signal_device / ifb_peer_wait_device with three ranks emulated on one GPU (flags are plain device
+    memory here; across processes they live in CUDA-IPC mapped peer memory)."""
+    import ctypes as C
+
+    world = 3
+    flags = [torch.zeros(64, dtype=torch.int32, device="cuda") for _ in range(world)]
+    arr = (C.c_void_p * world)(*[f.data_ptr() for f in flags])
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for epoch in (1, 2, 7):
+        for r in range(world):
+            nat.check(nat.lib().ifb_peer_signal_device(0, world, r, arr, epoch, st))
+        for r in range(world):
+            nat.check(nat.lib().ifb_peer_wait_device(0, world, C.c_void_p(flags[r].data_ptr()), epoch, st))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert flags[r][:world].tolist() == [epoch] * world
