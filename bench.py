@@ -98,6 +98,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def usable_cores():
+    """(threads to use, note): CPU affinity and cgroup CPU quota rather than the raw logical-CPU count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    note = f"{n} logical CPUs in the affinity mask"
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            q = float(quota) / float(period)
+            note += f", cgroup quota {q:.1f} CPUs"
+    except Exception:
+        pass
+    return max(1, n), note
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -135,7 +149,7 @@ def run_reference(args, wl_name, wl):
         return
     n, d, T, ns, ext = wl
     O = graft.load_oracle()
-    cores = os.cpu_count() or 1
+    cores, cores_note = usable_cores()
     train = mixture_numpy(min(TRAIN_ROWS, 1 << 18), d, 4242)
     tables = O.fit_forest(train, T, ns, random_seed=1, ext_level=ext)
     forest = O.Forest(tables)
@@ -163,7 +177,7 @@ def run_reference(args, wl_name, wl):
                    "note": "no JVM/Spark in this image: C port of the reference algorithm (oracle/ifb_oracle.c), "
                            "pthreads over all host cores, bounded sample per step"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port",
-                         "sample": f"{rows} rows x {d} features per step"},
+                         "sample": f"{rows} rows x {d} features per step", "cores_note": cores_note},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -312,12 +326,13 @@ def run_native(args, wl_name, wl):
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
         O = graft.load_oracle()
-        cores = os.cpu_count() or 1
+        cores, cores_note = usable_cores()
         tables = forest.export()
         sample = np.ascontiguousarray(X[: min(n, 4_000_000)].cpu().numpy())
         rate, rows, dt = cpu_port_rate(O, O.Forest(tables), sample, cores, target_s=12.0)
         line["cpu_baseline"] = {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port",
-                                "sample": f"first {rows} rows of the same matrix, same forest, {dt:.1f} s"}
+                                "sample": f"first {rows} rows of the same matrix, same forest, {dt:.1f} s",
+                                "cores_note": cores_note}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
