@@ -106,7 +106,8 @@ def usable_cores():
         quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
         if quota != "max":
             q = float(quota) / float(period)
-            note += f", cgroup quota {q:.1f} CPUs"
+            note += f", cgroup quota {q:.1f} CPUs (threads sized to the quota)"
+            n = min(n, max(1, int(np.ceil(q))))
     except Exception:
         pass
     return max(1, n), note
