@@ -1,0 +1,32 @@
+"""Small end-to-end invocation of every kernel family, meant to be run under compute-sanitizer."""
+import os, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g
+nat = g.load_package()._native
+O = g.load_oracle()
+rng = np.random.default_rng(0)
+
+def cm(X):
+    return torch.from_numpy(np.ascontiguousarray(X.T)).cuda().t()
+
+for (n, d, T, ext) in ((3000, 32, 20, -1), (1500, 128, 30, -1), (700, 900, 6, -1), (2500, 8, 10, 7), (2000, 64, 6, 63),
+                       (600, 256, 4, 255), (1200, 12, 5, 3)):
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    prm = nat.FitParams(T, min(256, n), d, 0, 1, 1, ext, 0, 0)
+    F = nat.fit_device(cm(X), prm)                                  # fit kernel
+    tb = F.export()
+    ref = O.Forest(tb).score(X, want_parts=True)
+    s, ds, ps = F.score_device(cm(X), want_parts=True)              # scoring kernels (col-major)
+    s2 = F.score_device(torch.from_numpy(X).cuda())                 # row-major (transpose / generic)
+    s3 = F.score_host(X)                                            # host pipeline
+    torch.cuda.synchronize()
+    assert np.array_equal(ds.cpu().numpy(), ref[1]), (n, d, T, ext)
+    assert np.max(np.abs(s.cpu().numpy() - ref[0]) / ref[0]) < 1e-12
+    assert np.max(np.abs(s2.cpu().numpy() - ref[0]) / ref[0]) < 1e-12 and np.max(np.abs(s3 - ref[0]) / ref[0]) < 1e-12
+    thr, frac = nat.quantile_device(s, 0.9)                         # radix select
+    lab = nat.predict_device(s, thr)
+    print("ok", n, d, T, ext, flush=True)
+print("sanitize_run done")
