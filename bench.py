@@ -35,6 +35,7 @@ WORKLOADS = {
     "config2": (10_000_000, 32, 100, 256, -1),
     "config3": (10_000_000, 64, 200, 256, 63),
     "config1": (1_000, 10, 100, 256, -1),
+    "config5": (1_000_000, 1024, 256, 256, 1023),   # BASELINE configs[4] per-GPU shape (named there on 4 GPUs)
 }
 TRAIN_ROWS = 1 << 20   # rows of the (rank-independent) training matrix the forest is fitted on
 FALLBACK_HBM_GBS = 6650.0
@@ -207,7 +208,10 @@ def run_native(args, wl_name, wl):
     fused = args.shard == "trees-fused" and world > 1
 
     # ---- setup (untimed): forest from the product's own GPU fit on a rank-independent training matrix ----
-    train = mixture_torch(torch, TRAIN_ROWS if n >= TRAIN_ROWS else max(n, ns), d, 4242, dev)
+    train_rows = TRAIN_ROWS if n >= TRAIN_ROWS else max(n, ns)
+    if d >= 512:
+        train_rows = min(train_rows, 1 << 17)   # the builder only samples numEstimators * numSamples rows anyway
+    train = mixture_torch(torch, train_rows, d, 4242, dev)
     t_lo, t_hi = (rank * T // world, (rank + 1) * T // world) if tree_sharded else (0, 0)
     prm = nat.FitParams(T, ns, d, 0, 1, 1, ext, t_lo, t_hi)
     torch.cuda.synchronize()
@@ -329,7 +333,7 @@ def run_native(args, wl_name, wl):
         O = graft.load_oracle()
         cores, cores_note = usable_cores()
         tables = forest.export()
-        sample = np.ascontiguousarray(X[: min(n, 4_000_000)].cpu().numpy())
+        sample = np.ascontiguousarray(X[: min(n, 4_000_000 if d <= 64 else 200_000)].cpu().numpy())
         rate, rows, dt = cpu_port_rate(O, O.Forest(tables), sample, cores, target_s=12.0)
         line["cpu_baseline"] = {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port",
                                 "sample": f"first {rows} rows of the same matrix, same forest, {dt:.1f} s",
