@@ -57,3 +57,27 @@ def test_product_never_references_oracle():
         for fn in fns:
             if fn.endswith((".py", ".cu", ".h", ".cpp", ".cc", "Makefile")):
                 assert "oracle" not in open(os.path.join(dp, fn), errors="ignore").read().lower(), os.path.join(dp, fn)
+
+
+def _build_c_consumer(tmp_path):
+    exe = tmp_path / "abi_smoke"
+    lib = os.path.join(ROOT, "isolation-forest_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", str(exe), "-L" + lib, "-lifb200",
+                           "-Wl,-rpath," + lib])
+    return exe
+
+
+def test_header_is_plain_c_and_links(nat, tmp_path):
+    """include/ifb200.h compiles as strict C99 and the library links from C (what a JNI stub needs)."""
+    exe = _build_c_consumer(tmp_path)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "abi_smoke ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_consumer_scores_on_gpu(nat, tmp_path):
+    exe = _build_c_consumer(tmp_path)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "GPU: path lengths 4.7488804 6.1433091" in out.stdout, out.stdout + out.stderr
