@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <queue>
 
@@ -351,27 +352,41 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
     // one chunk of trees (several passes, sums carried in path_sum between them).
     const int64_t need_whole = (total_nodes + 1) * 8 + (int64_t)T * 4;
     const int64_t need_one = (largest_tree + 1) * 8 + 64;
-    auto room_for = [&](int cand) { return (int64_t)smem_max - overhead - 2LL * (d + 1) * cand * 4; };
-    int R = 0;
-    for (int cand : {512, 256, 128, 64, 32})
-        if (room_for(cand) >= std::max(need_whole, need_one)) {
-            R = cand;
+    auto room_for = [&](int cand, int stages) { return (int64_t)smem_max - overhead - (int64_t)stages * (d + 1) * cand * 4; };
+    // Candidates in order of preference: (rows per tile = threads per CTA, ring depth).  Wide tiles matter more than
+    // double buffering: a tile keeps the CTA busy for tens of microseconds, its TMA fill costs ~1-3.
+    static const int kCand[][2] = {{512, 2}, {512, 1}, {256, 2}, {256, 1}, {128, 2}, {128, 1}, {64, 2}, {32, 2}};
+    static const bool single_ok = getenv("IFB_STD_NO_SINGLE_STAGE") == nullptr;
+    int R = 0, S = 2;
+    for (auto &c : kCand) {   // pass 1: the whole forest fits next to the tiles
+        if (c[1] == 1 && !single_ok) continue;
+        if (room_for(c[0], c[1]) >= std::max(need_whole, need_one)) {
+            R = c[0];
+            S = c[1];
             break;
         }
+    }
     if (R == 0)
-        for (int cand : {256, 128, 64, 32})
-            if (room_for(cand) >= std::max<int64_t>(64 * 1024, need_one)) {
-                R = cand;
+        for (auto &c : kCand) {   // pass 2: chunked forest, at least 64 KB of trees per pass, tiles of <= 256 rows
+            if (c[0] > 256 || (c[1] == 1 && !single_ok)) continue;
+            if (room_for(c[0], c[1]) >= std::max<int64_t>(64 * 1024, need_one)) {
+                R = c[0];
+                S = c[1];
                 break;
             }
-    if (R == 0 && room_for(32) >= need_one) R = 32;
-    if (R == 0) {  // rows too wide for two tile stages next to one tree: the generic kernel takes over
+        }
+    if (R == 0 && room_for(32, 2) >= need_one) {
+        R = 32;
+        S = 2;
+    }
+    if (R == 0) {  // rows too wide for a tile next to one tree: the generic kernel takes over
         delete p;
         *out = nullptr;
         return IFB_OK;
     }
+    p->stages = S;
     p->rows_per_tile = R;
-    const int64_t room = smem_max - overhead - 2LL * (d + 1) * R * 4;
+    const int64_t room = smem_max - overhead - (int64_t)S * (d + 1) * R * 4;
     // greedy chunking; each chunk: 1 pad word + nodes, plus 4 bytes per tree for the root table
     std::vector<float> val;
     std::vector<uint32_t> meta, roots(T, 0);

@@ -120,6 +120,7 @@ struct ifb_forest {
     struct StdPlan {
         int32_t d = -1;
         int32_t rows_per_tile = 0;
+        int32_t stages = 2;              // row-tile ring depth (1 when rows are wide: bigger tiles beat double buffering)
         std::vector<ifb::StdChunk> chunks;
         float *d_val = nullptr;
         uint32_t *d_meta = nullptr;

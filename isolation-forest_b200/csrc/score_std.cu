@@ -28,7 +28,7 @@ namespace ifb {
 
 namespace {
 
-constexpr int kStages = 2;
+constexpr int kMaxStages = 2;
 constexpr int kMaxTopTrees = 256;   // trees per chunk whose two top levels ride in the kernel parameters
 
 // Levels 0 and 1 of every tree of the chunk, passed as a kernel parameter (constant bank): all 32 lanes of a
@@ -117,7 +117,7 @@ struct SmemLayout {
     uint32_t tiles;   // kStages * R * (d+1) f32, 128-byte aligned
     uint32_t total;
 };
-__host__ __device__ inline SmemLayout make_layout(int n_trees, int chunk_words, int R, int d) {
+__host__ __device__ inline SmemLayout make_layout(int n_trees, int chunk_words, int R, int d, int kStages) {
     SmemLayout L;
     L.bars = 0;
     L.roots = 64;
@@ -147,7 +147,7 @@ __device__ __forceinline__ uint32_t walk_step(uint32_t node, uint32_t val_s, uin
     return next;
 }
 
-template <int R, int C, bool USE_TMA, bool WANT_DEPTH, int DEEP>
+template <int R, int C, bool USE_TMA, bool WANT_DEPTH, int DEEP, int kStages>
 __global__ void __launch_bounds__(R, 1)
 score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_rem,
                  const __grid_constant__ TopTable top, const ScoreStdParams p) {
@@ -155,7 +155,7 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
     constexpr int NSUB = R / RB;
     constexpr uint32_t COL_BYTES = RB * 4;
     extern __shared__ __align__(1024) unsigned char smem[];
-    const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, p.d);
+    const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, p.d, kStages);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
     const int tid = threadIdx.x;
     const int d = p.d;
@@ -220,7 +220,7 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
     if constexpr (USE_TMA) {
         if (tid == 0) {
             if (tile < p.n_tiles) issue_tile(tile, 0);
-            if (tile + stride < p.n_tiles) issue_tile(tile + stride, 1);
+            if (kStages > 1 && tile + stride < p.n_tiles) issue_tile(tile + stride, 1);
         }
     }
 
@@ -233,9 +233,9 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
     const uint32_t leaf_col = (uint32_t)d * COL_BYTES;
 
     for (int64_t k = 0; tile < p.n_tiles; tile += stride, ++k) {
-        const int stage = (int)(k & 1);
+        const int stage = kStages > 1 ? (int)(k & 1) : 0;
         if constexpr (USE_TMA) {
-            mbar_wait(&bars[stage], (uint32_t)((k >> 1) & 1));
+            mbar_wait(&bars[stage], kStages > 1 ? (uint32_t)((k >> 1) & 1) : (uint32_t)(k & 1));
         } else {
             load_tile_plain(tile, stage);
             __syncthreads();
@@ -322,7 +322,7 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
         }
         __syncthreads();  // every read of this stage is done before it is refilled
         if constexpr (USE_TMA) {
-            if (tid == 0 && tile + 2 * stride < p.n_tiles) issue_tile(tile + 2 * stride, stage);
+            if (tid == 0 && tile + kStages * stride < p.n_tiles) issue_tile(tile + kStages * stride, stage);
         }
     }
 }
@@ -366,7 +366,7 @@ int make_tmap(CUtensorMap *map, const float *X, int64_t n_rows, int32_t d, int64
     return IFB_OK;
 }
 
-template <int R, int C>
+template <int R, int C, int S>
 int launch_variant(bool use_tma, bool want_depth, const CUtensorMap &m0, const CUtensorMap &m1, const TopTable &top,
                    const ScoreStdParams &p, int grid, size_t smem, cudaStream_t stream) {
     auto go = [&](auto kern) -> int {
@@ -377,10 +377,10 @@ int launch_variant(bool use_tma, bool want_depth, const CUtensorMap &m0, const C
         return IFB_OK;
     };
     const bool deep6 = p.max_depth == 8 && !want_depth && use_tma;
-    if (deep6) return go(score_std_kernel<R, C, true, false, 6>);
+    if (deep6) return go(score_std_kernel<R, C, true, false, 6, S>);
     if (use_tma)
-        return want_depth ? go(score_std_kernel<R, C, true, true, -1>) : go(score_std_kernel<R, C, true, false, -1>);
-    return want_depth ? go(score_std_kernel<R, C, false, true, -1>) : go(score_std_kernel<R, C, false, false, -1>);
+        return want_depth ? go(score_std_kernel<R, C, true, true, -1, S>) : go(score_std_kernel<R, C, true, false, -1, S>);
+    return want_depth ? go(score_std_kernel<R, C, false, true, -1, S>) : go(score_std_kernel<R, C, false, false, -1, S>);
 }
 
 }  // namespace
@@ -518,15 +518,25 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
         p.n_tiles = n_tiles;
         if (scatter) p.scatter = *scatter; else p.scatter.world = 0;
         p.finalize_scatter = (scatter && ci + 1 == n_chunks) ? 1 : 0;
-        const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, d);
+        const int S = plan->stages;
+        const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, d, S);
         const TopTable &top = *reinterpret_cast<const TopTable *>(plan->h_top.data() + (size_t)ci * sizeof(TopTable));
         int rc;
         switch (R) {
-            case 512: rc = launch_variant<512, 4>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
-            case 256: rc = launch_variant<256, 8>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
-            case 128: rc = launch_variant<128, 16>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
-            case 64: rc = launch_variant<64, 16>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
-            default: rc = launch_variant<32, 16>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
+            case 512:
+                rc = S == 2 ? launch_variant<512, 4, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
+                            : launch_variant<512, 4, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream);
+                break;
+            case 256:
+                rc = S == 2 ? launch_variant<256, 8, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
+                            : launch_variant<256, 8, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream);
+                break;
+            case 128:
+                rc = S == 2 ? launch_variant<128, 16, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
+                            : launch_variant<128, 16, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream);
+                break;
+            case 64: rc = launch_variant<64, 16, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
+            default: rc = launch_variant<32, 16, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream); break;
         }
         if (rc) return rc;
     }
