@@ -355,10 +355,14 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
     auto room_for = [&](int cand, int stages) { return (int64_t)smem_max - overhead - (int64_t)stages * (d + 1) * cand * 4; };
     // Candidates in order of preference: (rows per tile = threads per CTA, ring depth).  Wide tiles matter more than
     // double buffering: a tile keeps the CTA busy for tens of microseconds, its TMA fill costs ~1-3.
-    static const int kCand[][2] = {{512, 2}, {512, 1}, {256, 2}, {256, 1}, {128, 2}, {128, 1}, {64, 2}, {32, 2}};
+    static const bool try1024 = getenv("IFB_STD_NO_1024") == nullptr;
+    const int kCandAll[][2] = {{1024, 1}, {512, 2}, {512, 1}, {256, 2}, {256, 1}, {128, 2}, {128, 1}, {64, 2}, {32, 2}};
+    const int (*kCand)[2] = try1024 ? kCandAll : kCandAll + 1;
+    const int nCand = try1024 ? 9 : 8;
     static const bool single_ok = getenv("IFB_STD_NO_SINGLE_STAGE") == nullptr;
     int R = 0, S = 2;
-    for (auto &c : kCand) {   // pass 1: the whole forest fits next to the tiles
+    for (int ci = 0; ci < nCand; ci++) {   // pass 1: the whole forest fits next to the tiles
+        const int *c = kCand[ci];
         if (c[1] == 1 && !single_ok) continue;
         if (room_for(c[0], c[1]) >= std::max(need_whole, need_one)) {
             R = c[0];
@@ -367,7 +371,8 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
         }
     }
     if (R == 0)
-        for (auto &c : kCand) {   // pass 2: chunked forest, at least 64 KB of trees per pass, tiles of <= 256 rows
+        for (int ci = 0; ci < nCand; ci++) {   // pass 2: chunked forest, >= 64 KB of trees per pass, tiles of <= 256 rows
+            const int *c = kCand[ci];
             if (c[0] > 256 || (c[1] == 1 && !single_ok)) continue;
             if (room_for(c[0], c[1]) >= std::max<int64_t>(64 * 1024, need_one)) {
                 R = c[0];

@@ -523,6 +523,13 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
         const TopTable &top = *reinterpret_cast<const TopTable *>(plan->h_top.data() + (size_t)ci * sizeof(TopTable));
         int rc;
         switch (R) {
+            case 1024: {
+                static const int c1024 = getenv("IFB_STD_1024") ? atoi(getenv("IFB_STD_1024")) : 4;
+                rc = c1024 == 4 ? launch_variant<1024, 4, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
+                   : c1024 == 3 ? launch_variant<1024, 3, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
+                                : launch_variant<1024, 2, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream);
+                break;
+            }
             case 512:
                 rc = S == 2 ? launch_variant<512, 4, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
                             : launch_variant<512, 4, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream);
