@@ -82,12 +82,6 @@ struct WideNode {
     int32_t slot;      // own weight slot (-1 at leaves)
 };
 
-struct ExtTreeDesc {          // one per tree, extended forests
-    int64_t node_begin;       // first node (BFS order) in the device arrays
-    int32_t node_count;
-    int32_t depth;            // deepest leaf
-};
-
 }  // namespace ifb
 
 struct ifb_forest {

@@ -55,7 +55,6 @@ struct ScoreStdParams {
     int32_t rem_d;           // features in the trailing partial box (0 = none)
     const float *val;        // chunk tables in global memory
     const uint32_t *meta;
-    const uint32_t *roots;   // byte offsets of the chunk's tree roots inside val[]
     int32_t chunk_words;
     int32_t n_trees;         // trees in this chunk
     int32_t max_depth;
@@ -504,7 +503,6 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
         p.rem_d = rem_d;
         p.val = plan->d_val + c.node_begin;
         p.meta = plan->d_meta + c.node_begin;
-        p.roots = nullptr;
         p.chunk_words = c.node_count;
         p.n_trees = c.tree_end - c.tree_begin;
         p.max_depth = f->max_depth;
