@@ -160,3 +160,30 @@ def test_cpp_host_program(pkg, tmp_path):
     out = subprocess.run([str(exe), str(tmp_path / "model")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "host_roundtrip ok" in out.stdout
+
+
+def test_bootstrap_maxfeatures_and_partitions_reach_the_builder(pkg, oracle, mammography):
+    """bootstrap / maxFeatures / the P of the tree-seed formula flow from the Estimator params into the GPU builder:
+    forests equal the oracle's restatement with the same resolved values (IF/core/SharedTrainLogic.scala:33-60,
+    IF/IsolationForest.scala:76-78)."""
+    X, _ = mammography
+    X32 = X.astype(np.float32)
+    cases = [
+        (dict(setBootstrap=True), dict(bootstrap=True)),
+        (dict(setMaxFeatures=0.5), dict(num_features=3)),          # floor(0.5 * 6)
+        (dict(setMaxFeatures=4.0), dict(num_features=4)),          # > 1.0 is a count
+        (dict(setNumPartitions=4), dict(num_partitions=4)),
+        (dict(setMaxSamples=0.01), dict()),                         # fraction of N: floor(0.01 * 11183) = 111 samples
+    ]
+    for setters, okw in cases:
+        est = pkg.IsolationForest().setNumEstimators(12).setRandomSeed(9)
+        for k, v in setters.items():
+            getattr(est, k)(v)
+        m = est.fit(X)
+        ns = 111 if "setMaxSamples" in setters else 256
+        ref = oracle.fit_forest(X32, 12, ns, random_seed=9, **okw)
+        got = m.tables()
+        for key in ("node_off", "left", "right", "feature", "threshold", "num_instances"):
+            assert np.array_equal(got[key], ref[key]), (setters, key)
+        assert m.getNumSamples() == ns
+        assert m.getNumFeatures() == okw.get("num_features", 6)
