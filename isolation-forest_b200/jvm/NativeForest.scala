@@ -15,33 +15,31 @@ final case class ForestTables(
   threshold: Array[Double], numInstances: Array[Long])
 
 object ForestTables {
-  /** Same traversal as NodeData.build (IsolationForestModelReadWrite.scala:82-132). */
+  /** Same pre-order numbering as NodeData.build (IsolationForestModelReadWrite.scala:82-132). */
   def fromTrees(trees: Array[IsolationTree]): ForestTables = {
-    val off = Array.newBuilder[Int]; off += 0
-    val l = Array.newBuilder[Int]; val r = Array.newBuilder[Int]; val f = Array.newBuilder[Int]
-    val t = Array.newBuilder[Double]; val n = Array.newBuilder[Long]
-    var total = 0
+    import scala.collection.mutable.ArrayBuffer
+    val off = ArrayBuffer(0)
+    val l = ArrayBuffer.empty[Int]; val r = ArrayBuffer.empty[Int]; val f = ArrayBuffer.empty[Int]
+    val t = ArrayBuffer.empty[Double]; val n = ArrayBuffer.empty[Long]
     trees.foreach { tree =>
-      var next = 0
-      def visit(node: Node): Int = node match {
+      val base = l.length
+      def visit(node: Node): Int = node match { // returns the tree-local id of `node`
         case ExternalNode(numInstances) =>
-          val id = next; next += 1
-          l += -1; r += -1; f += -1; t += 0.0; n += numInstances; id
+          val id = l.length - base
+          l += -1; r += -1; f += -1; t += 0.0; n += numInstances
+          id
         case InternalNode(leftChild, rightChild, splitAttribute, splitValue) =>
-          val id = next; next += 1
-          val slot = total + id
+          val id = l.length - base
           l += (id + 1); r += -1; f += splitAttribute; t += splitValue; n += -1L
           visit(leftChild)
-          val rid = visit(rightChild)
-          patchRight(slot, rid)
+          r(base + id) = visit(rightChild)
           id
       }
-      // (right-child ids are patched after the subtree is numbered; omitted helper keeps an ArrayBuffer)
-      visit(tree.node); total += next; off += total
+      visit(tree.node)
+      off += l.length
     }
-    ForestTables(off.result(), l.result(), r.result(), f.result(), t.result(), n.result())
+    ForestTables(off.toArray, l.toArray, r.toArray, f.toArray, t.toArray, n.toArray)
   }
-  private def patchRight(slot: Int, rid: Int): Unit = () // see comment above
 }
 
 private[isolationforest] object NativeForest {
