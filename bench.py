@@ -36,7 +36,11 @@ WORKLOADS = {
     "config3": (10_000_000, 64, 200, 256, 63),
     "config1": (1_000, 10, 100, 256, -1),
     "config5": (1_000_000, 1024, 256, 256, 1023),   # BASELINE configs[4] per-GPU shape (named there on 4 GPUs)
+    # BASELINE configs[3]: fit+transform, every step builds the forest on the step's rows and scores them
+    # (use --shard trees / trees-fused under torchrun for the 8-GPU tree-sharded layout it names)
+    "config4": (100_000_000, 128, 512, 256, -1),
 }
+FIT_IN_STEP = {"config4"}
 TRAIN_ROWS = 1 << 20   # rows of the (rank-independent) training matrix the forest is fitted on
 FALLBACK_HBM_GBS = 6650.0
 
@@ -221,6 +225,9 @@ def run_native(args, wl_name, wl):
     fit_ms = (time.perf_counter() - t0) * 1e3
     del train
     X = mixture_torch(torch, n, d, 1002 + (0 if tree_sharded else rank), dev)
+    fit_in_step = wl_name in FIT_IN_STEP
+    holder = {"forest": forest}
+    phase_events = []
     scores = torch.empty(n, dtype=torch.float64, device=dev)
     psum = torch.zeros(n, dtype=torch.float32, device=dev) if tree_sharded else None
     ctx = None
@@ -230,6 +237,13 @@ def run_native(args, wl_name, wl):
         scores = torch.empty(ctx.rows_local, dtype=torch.float64, device=dev)
 
     def step():
+        forest = holder["forest"]
+        if fit_in_step:     # Estimator.fit on this step's rows (own tree slice when trees are sharded), then transform
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            forest = holder["forest"] = nat.fit_device(X, prm)
+            ev[1].record()
+            phase_events.append(ev)
         if fused:
             ctx.score(forest, X, T, ns, scores_local=scores)   # kernel scatters partial sums into peer memory
         elif tree_sharded:
@@ -239,6 +253,8 @@ def run_native(args, wl_name, wl):
             nat.finalize_scores_device(psum, T, ns, scores=scores)
         else:
             forest.score_device(X, scores=scores)
+        if fit_in_step:
+            ev[2].record()
 
     def barrier():
         if world > 1:
@@ -252,6 +268,7 @@ def run_native(args, wl_name, wl):
     if rank == 0:
         sampler.start()
     nat.kernel_launch_count(reset=True)
+    phase_events.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -266,17 +283,21 @@ def run_native(args, wl_name, wl):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     rows_job = n * (1 if tree_sharded else world)
+    phases = None
+    if phase_events:
+        phases = {"fit_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in phase_events])),
+                  "transform_ms": float(np.mean([e[1].elapsed_time(e[2]) for e in phase_events]))}
     value = rows_job * args.steps / (ms_total / 1e3)
 
     # ---- e2e: the call a Spark task would make: host buffers in, host scores out ----------------------
     e2e = None
-    if not tree_sharded:
+    if not tree_sharded and n * d * 4 <= (8 << 30):
         hx = nat.PinnedBuffer((d, n), np.float32)              # column-major rows x features
         hs = nat.PinnedBuffer((n,), np.float64)
         torch.from_numpy(hx.array).copy_(X.t())                # fill the pinned staging buffer (untimed)
         torch.cuda.synchronize()
         import ctypes as C
-        args_host = (forest.handle, C.c_void_p(hx.array.ctypes.data), n, d, n, nat.COL_MAJOR,
+        args_host = (holder["forest"].handle, C.c_void_p(hx.array.ctypes.data), n, d, n, nat.COL_MAJOR,
                      C.c_void_p(hs.array.ctypes.data), None, None)
         for _ in range(2):
             nat.check(nat.lib().ifb_score_host(*args_host))
@@ -304,14 +325,15 @@ def run_native(args, wl_name, wl):
     kernel_ms = ms_total / args.steps                    # one step == one launch of the dominant kernel
     alg_bytes = n * (4 * d + 8)
     achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
-    info = forest.info()
+    info = holder["forest"].info()
     line = {
         "metric": "rows scored/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "strong" if tree_sharded else "weak", "vs_baseline": None,
         "dtype": "f32 features, f32 path sums, f64 scores" + (", f64 hyperplane dots" if ext >= 0 else ""),
         "data": "synthetic",
-        "config": {"workload": f"{wl_name}: IsolationForestModel.transform {n}x{d} f32 per GPU, {T} trees, "
+        "config": {"workload": f"{wl_name}: " + ("IsolationForest.fit + " if fit_in_step else "") +
+                               f"IsolationForestModel.transform {n}x{d} f32 per GPU, {T} trees, "
                                f"maxSamples={ns}" + (f", extensionLevel={ext}" if ext >= 0 else ""),
                    "parallelism": (f"trees sharded x{world}, partial sums scattered into NVLink peer memory by the scoring kernel"
                                    if fused else f"trees sharded x{world} + NCCL all-reduce of path sums" if tree_sharded else
@@ -325,8 +347,15 @@ def run_native(args, wl_name, wl):
                      "traffic": ncu_traffic(wl_name), "peak_source": peak_src,
                      "kernel": "score_ext_*" if ext >= 0 else "score_std_kernel",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
-                     "note": "per GPU; one step = one launch of the dominant kernel"},
+                     "note": "per GPU; one step = one launch of the dominant kernel"
+                             + (" (+ the fit launch and its host-side table assembly)" if fit_in_step else "")},
     }
+    if phases:
+        line["phases"] = phases
+        # the roofline object describes the scoring kernel alone
+        line["roofline"].update(kernel_ms=phases["transform_ms"],
+                                achieved=alg_bytes / (phases["transform_ms"] / 1e3) / 1e9,
+                                frac=alg_bytes / (phases["transform_ms"] / 1e3) / 1e9 / peak)
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
@@ -334,6 +363,7 @@ def run_native(args, wl_name, wl):
         cores, cores_note = usable_cores()
         tables = forest.export()
         sample = np.ascontiguousarray(X[: min(n, 4_000_000 if d <= 64 else 200_000)].cpu().numpy())
+        forest = holder["forest"]
         rate, rows, dt = cpu_port_rate(O, O.Forest(tables), sample, cores, target_s=12.0)
         line["cpu_baseline"] = {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port",
                                 "sample": f"first {rows} rows of the same matrix, same forest, {dt:.1f} s",
