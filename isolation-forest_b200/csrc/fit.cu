@@ -13,8 +13,12 @@
 // warp-shuffle reductions and ballot/popc scans.  This translation unit is compiled with -fmad=false:
 // the JVM never contracts a*b+c, so neither may the f64 split arithmetic here.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "ifb_internal.h"
@@ -53,6 +57,10 @@ struct FitDev {
     int32_t *e_idx;              // [k]
     double *e_raw;               // [k]
     float *e_w, *e_mn, *e_mx;    // [k]
+    // staging (see "staged sample" below)
+    int32_t small_in_smem;       // per-tree scratch lists live in shared memory
+    int32_t stage;               // 0: read X through rows[]; 1: sample staged in shared memory; 2: in `sample`
+    float *sample;               // [trees][d][n] staged sample when stage == 2
 };
 
 // ---- java.util.Random ---------------------------------------------------------------------------
@@ -177,6 +185,18 @@ __device__ __forceinline__ float feat_value(const FitDev &p, long long row, int 
     return p.layout == IFB_COL_MAJOR ? __ldg(p.X + (long long)f * p.ld + row) : __ldg(p.X + row * p.ld + f);
 }
 
+// Value of feature f of the tree's sample slot pr.  The tree's n sampled rows are staged once, feature-major
+// ([f][slot]), in shared memory (or an L2-resident scratch) so that the hundreds of min/max and partition passes of a
+// tree never go back to the (possibly 50 GB, TLB-hostile) training matrix.
+struct SampleView {
+    const FitDev &p;
+    const float *S;        // staged sample or nullptr
+    const int64_t *rows;   // slot -> training row
+    __device__ __forceinline__ float operator()(int pr, int f) const {
+        return S ? S[(long long)f * p.n + pr] : feat_value(p, rows[pr], f);
+    }
+};
+
 struct NodeTask {
     int32_t start, count, height, parent, is_right;
 };
@@ -195,11 +215,11 @@ struct Shared {
 };
 
 // block-wide min/max of feature f over rows perm[start .. start+count)
-__device__ void block_min_max(const FitDev &p, Shared &sh, const int32_t *perm, const int64_t *rows, int start,
-                              int count, int f, float &mn_out, float &mx_out) {
+__device__ void block_min_max(const SampleView &val, Shared &sh, const int32_t *perm, int start, int count, int f,
+                              float &mn_out, float &mx_out) {
     float mn = INFINITY, mx = -INFINITY;
     for (int i = threadIdx.x; i < count; i += BT) {
-        const float v = feat_value(p, rows[perm[start + i]], f);
+        const float v = val(perm[start + i], f);
         // Scala's `if (v < mn) mn = v; if (v > mx) mx = v` (NaN never replaces)
         if (v < mn) mn = v;
         if (v > mx) mx = v;
@@ -273,6 +293,8 @@ __device__ void block_partition(Shared &sh, int32_t *perm, int32_t *perm2, int s
     __syncthreads();
 }
 
+extern __shared__ __align__(16) unsigned char fit_arena[];
+
 template <bool EXT>
 __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
     __shared__ Shared sh;
@@ -283,11 +305,46 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
     const long long tree_seed = p.random_seed + 2LL * ((long long)p.num_partitions + 1) + tree_id;
 
     int64_t *rows = p.rows + (int64_t)tl * p.n;
-    int32_t *perm = p.perm + (int64_t)tl * p.n, *perm2 = p.perm2 + (int64_t)tl * p.n;
-    int64_t *hkeys = p.hkeys + (int64_t)tl * p.hcap, *hvals = p.hvals + (int64_t)tl * p.hcap;
-    int32_t *feat_perm = p.feat_perm + (int64_t)tl * p.d;
-    int32_t *feat_idx = p.feat_idx + (int64_t)tl * p.num_features;
-    int32_t *avail = p.avail + (int64_t)tl * p.num_features;
+    int32_t *perm, *perm2, *feat_perm, *feat_idx, *avail, *e_idx = nullptr;
+    int64_t *hkeys, *hvals;
+    double *e_raw = nullptr;
+    float *e_w = nullptr, *e_mn = nullptr, *e_mx = nullptr;
+    float *stage_buf = nullptr;
+    if (p.small_in_smem) {   // carve the arena: 8-byte arrays first (same order as fit_smem_layout on the host)
+        unsigned char *a = fit_arena;
+        hkeys = (int64_t *)a; a += (size_t)p.hcap * 8;
+        hvals = (int64_t *)a; a += (size_t)p.hcap * 8;
+        e_raw = (double *)a; a += (size_t)(EXT ? p.k : 0) * 8;
+        perm = (int32_t *)a; a += (size_t)p.n * 4;
+        perm2 = (int32_t *)a; a += (size_t)p.n * 4;
+        feat_perm = (int32_t *)a; a += (size_t)p.d * 4;
+        feat_idx = (int32_t *)a; a += (size_t)p.num_features * 4;
+        avail = (int32_t *)a; a += (size_t)p.num_features * 4;
+        if (EXT) {
+            e_idx = (int32_t *)a; a += (size_t)p.k * 4;
+            e_w = (float *)a; a += (size_t)p.k * 4;
+            e_mn = (float *)a; a += (size_t)p.k * 4;
+            e_mx = (float *)a; a += (size_t)p.k * 4;
+        }
+        a = (unsigned char *)(((uintptr_t)a + 15) & ~(uintptr_t)15);
+        if (p.stage == 1) stage_buf = (float *)a;
+    } else {
+        perm = p.perm + (int64_t)tl * p.n;
+        perm2 = p.perm2 + (int64_t)tl * p.n;
+        hkeys = p.hkeys + (int64_t)tl * p.hcap;
+        hvals = p.hvals + (int64_t)tl * p.hcap;
+        feat_perm = p.feat_perm + (int64_t)tl * p.d;
+        feat_idx = p.feat_idx + (int64_t)tl * p.num_features;
+        avail = p.avail + (int64_t)tl * p.num_features;
+        if (EXT) {
+            e_idx = p.e_idx + (int64_t)tl * p.k;
+            e_raw = p.e_raw + (int64_t)tl * p.k;
+            e_w = p.e_w + (int64_t)tl * p.k;
+            e_mn = p.e_mn + (int64_t)tl * p.k;
+            e_mx = p.e_mx + (int64_t)tl * p.k;
+        }
+    }
+    if (p.stage == 2) stage_buf = p.sample + (int64_t)tl * p.d * p.n;
     int32_t *o_left = p.left + (int64_t)tl * p.cap, *o_right = p.right + (int64_t)tl * p.cap;
     int64_t *o_ninst = p.num_instances + (int64_t)tl * p.cap;
 
@@ -337,6 +394,23 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
         sh.stack[0] = NodeTask{0, p.n, 0, -1, 0};
     }
     __syncthreads();
+    // ---- stage the tree's sample, feature-major: stage_buf[f][slot] = X(rows[slot], f) ---------------
+    if (stage_buf) {
+        const long long total = (long long)p.d * p.n;
+        if (p.layout == IFB_COL_MAJOR) {
+            for (long long e = tid; e < total; e += BT) {
+                const int f = (int)(e / p.n), i = (int)(e - (long long)f * p.n);
+                stage_buf[e] = __ldg(p.X + (long long)f * p.ld + rows[i]);
+            }
+        } else {
+            for (long long e = tid; e < total; e += BT) {
+                const int i = (int)(e / p.d), f = (int)(e - (long long)i * p.d);
+                stage_buf[(long long)f * p.n + i] = __ldg(p.X + rows[i] * p.ld + f);
+            }
+        }
+        __syncthreads();
+    }
+    const SampleView val{p, stage_buf, rows};
 
     int sp = 1;        // thread 0 only
     int nnodes = 0;    // thread 0 only
@@ -360,6 +434,32 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
 
         if (!EXT) {
             // getFeatureToSplit runs before the stop test and consumes draws (IF/IsolationTree.scala:124-156)
+            // A node with at most one row can never find a feature with min != max (unless the row holds a NaN:
+            // then min/max stay at +/-inf and the general loop below decides): every feature of the subset is
+            // tried and rejected, i.e. the only effect is nextInt(m) for m = numFeatures .. 1 on the tree's stream.
+            // Thread 0 replays exactly those draws without the per-trial block reductions.
+            bool fast_leaf = cur.count <= 1;
+            if (fast_leaf && cur.count == 1) {
+                const int pr = perm[cur.start];
+                int has_nan = 0;
+                for (int i = tid; i < p.num_features; i += BT) {
+                    const float v = val(pr, feat_idx[i]);
+                    has_nan |= (v != v) ? 1 : 0;
+                }
+                fast_leaf = __syncthreads_or(has_nan) == 0;
+            }
+            if (fast_leaf) {
+                if (tid == 0) {
+                    for (int m = p.num_features; m >= 1; m--) (void)jr_next_int(rnd, m);
+                    o_left[id] = -1;
+                    o_right[id] = -1;
+                    (p.feature + (int64_t)tl * p.cap)[id] = -1;
+                    (p.threshold + (int64_t)tl * p.cap)[id] = 0.0;
+                    o_ninst[id] = cur.count;
+                }
+                __syncthreads();   // every thread has consumed sh.cur / sh.id before thread 0 pops the next task
+                continue;
+            }
             for (int i = tid; i < p.num_features; i += BT) avail[i] = feat_idx[i];
             if (tid == 0) sh.found = 0;
             __syncthreads();
@@ -379,7 +479,7 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
                 if (trial < 0) break;
                 n_avail--;
                 float mn = 0.f, mx = 0.f;
-                if (cur.count > 0) block_min_max(p, sh, perm, rows, cur.start, cur.count, trial, mn, mx);
+                if (cur.count > 0) block_min_max(val, sh, perm, cur.start, cur.count, trial, mn, mx);
                 if (tid == 0 && cur.count > 0) {
                     const double dmn = (double)mn, dmx = (double)mx;
                     if (dmn != dmx) {
@@ -414,7 +514,7 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
             // left = x < split (f32 widened, strict); everything else goes right.  (The reference filters
             // right with x >= split, dropping NaN rows; NaN training features are outside the contract.)
             block_partition(sh, perm, perm2, cur.start, cur.count,
-                            [&](int32_t pr) { return (double)feat_value(p, rows[pr], f) < split; });
+                            [&](int32_t pr) { return (double)val(pr, f) < split; });
             if (tid == 0) {
                 const int nl = sh.nl;
                 sh.stack[sp++] = NodeTask{cur.start + nl, cur.count - nl, cur.height + 1, id, 1};
@@ -425,9 +525,6 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
             // ---- extended: IF/extended/ExtendedIsolationTree.scala:139-260 -----------------------
             double *o_off = p.offset + (int64_t)tl * p.cap;
             int32_t *o_slot = p.hp_slot + (int64_t)tl * p.cap;
-            int32_t *e_idx = p.e_idx + (int64_t)tl * p.k;
-            double *e_raw = p.e_raw + (int64_t)tl * p.k;
-            float *e_w = p.e_w + (int64_t)tl * p.k, *e_mn = p.e_mn + (int64_t)tl * p.k, *e_mx = p.e_mx + (int64_t)tl * p.k;
             const int dim = p.num_features;
             const int nnz = p.k;  // min(extensionLevel + 1, dim)
             if (tid == 0) sh.leaf = (cur.height >= p.height_limit || cur.count <= 1) ? 1 : 0;  // :152-153
@@ -470,7 +567,7 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
                     const int j = e_idx[kk];
                     float mn = INFINITY, mx = -INFINITY;
                     for (int i = lane; i < cur.count; i += 32) {
-                        const float v = feat_value(p, rows[perm[cur.start + i]], j);
+                        const float v = val(perm[cur.start + i], j);
                         if (v < mn) mn = v;
                         if (v > mx) mx = v;
                     }
@@ -514,10 +611,9 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
             __syncthreads();
             const double off = sh.offset;
             block_partition(sh, perm, perm2, cur.start, cur.count, [&](int32_t pr) {      // :230-232
-                const long long row = rows[pr];
                 double sum = 0.0;
                 for (int q = 0; q < nnz; q++) {
-                    const float prod = __fmul_rn(h_w[q], feat_value(p, row, h_idx[q]));
+                    const float prod = __fmul_rn(h_w[q], val(pr, h_idx[q]));
                     sum = sum + (double)prod;
                 }
                 return sum < off;
@@ -554,6 +650,29 @@ struct DevBuf {
     template <typename T>
     T *as() { return reinterpret_cast<T *>(p); }
 };
+
+// Pinned host staging block shared by the fit calls of this process (copy + compaction phase is serialised).
+struct PinnedStage {
+    std::mutex mu;
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {   // caller holds mu
+        if (bytes <= cap) return IFB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("pinned staging allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            return IFB_ENOMEM;
+        }
+        cap = want;
+        return IFB_OK;
+    }
+};
+PinnedStage g_stage;
 
 // heightLimit = ceil(log10(n)/log10(2))  (IF/IsolationTree.scala:60-61)
 int height_limit_of(int32_t n) { return (int)std::ceil(std::log10((double)n) / std::log10(2.0)); }
@@ -603,6 +722,13 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     DeviceGuard dg(device);
     cudaStream_t stream = (cudaStream_t)stream_;
 
+    // IFB_FIT_TIMING=1 (diagnostic): wall-clock phases of this call on stderr
+    const bool timing = std::getenv("IFB_FIT_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(now() - t).count();
+    };
+    const auto t_start = now();
     const int n = prm->num_samples;
     const int hl = height_limit_of(n);
     IFB_REQUIRE(hl <= 32, "height limit %d too large", hl);
@@ -653,31 +779,77 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     p.e_idx = b_eidx.as<int32_t>(); p.e_raw = b_eraw.as<double>(); p.e_w = b_ew.as<float>();
     p.e_mn = b_emn.as<float>(); p.e_mx = b_emx.as<float>();
 
+    // shared-memory arena (must mirror the carve-up at the top of fit_kernel)
+    const size_t small_bytes = (size_t)hcap * 16 + (ext ? (size_t)k * 8 : 0) +
+                               4 * ((size_t)2 * n + d + 2 * (size_t)prm->num_features + (ext ? 4 * (size_t)k : 0));
+    const size_t small_aligned = (small_bytes + 15) & ~(size_t)15;
+    const size_t sample_bytes = (size_t)d * n * 4;
+    constexpr size_t kSmallMax = 64 << 10, kArenaMax = 200 << 10, kScratchMax = (size_t)2 << 30;
+    const bool no_stage = std::getenv("IFB_FIT_NO_STAGE") != nullptr;   // test hook: the unstaged path
+    p.small_in_smem = small_bytes <= kSmallMax && !no_stage;
+    p.stage = 0;
+    DevBuf b_sample(stream);
+    if (!no_stage) {
+        if (p.small_in_smem && small_aligned + sample_bytes <= kArenaMax) p.stage = 1;
+        else if (T * sample_bytes <= kScratchMax) {
+            p.stage = 2;
+            if ((rc = b_sample.alloc(T * sample_bytes))) return rc;
+            p.sample = b_sample.as<float>();
+        }
+    }
+    const size_t dyn = p.small_in_smem ? small_aligned + (p.stage == 1 ? sample_bytes : 0) : 0;
     if (ntrees > 0) {
-        if (ext) fit_kernel<true><<<ntrees, BT, 0, stream>>>(p);
-        else fit_kernel<false><<<ntrees, BT, 0, stream>>>(p);
+        if (ext) {
+            IFB_CUDA(cudaFuncSetAttribute(fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            fit_kernel<true><<<ntrees, BT, dyn, stream>>>(p);
+        } else {
+            IFB_CUDA(cudaFuncSetAttribute(fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            fit_kernel<false><<<ntrees, BT, dyn, stream>>>(p);
+        }
         IFB_CUDA(cudaGetLastError());
         count_launch();
     }
-    // node tables back to the host, compacted into the persisted layout
-    std::vector<int32_t> n_nodes(T), n_int(T), left(T * cap), right(T * cap), feature, slot;
-    std::vector<int64_t> ninst(T * cap);
-    std::vector<double> thr, off;
-    IFB_CUDA(cudaMemcpyAsync(n_nodes.data(), p.n_nodes, T * 4, cudaMemcpyDeviceToHost, stream));
-    IFB_CUDA(cudaMemcpyAsync(left.data(), p.left, T * cap * 4, cudaMemcpyDeviceToHost, stream));
-    IFB_CUDA(cudaMemcpyAsync(right.data(), p.right, T * cap * 4, cudaMemcpyDeviceToHost, stream));
-    IFB_CUDA(cudaMemcpyAsync(ninst.data(), p.num_instances, T * cap * 8, cudaMemcpyDeviceToHost, stream));
+    if (timing) {
+        const double t_launch = ms_since(t_start);
+        cudaStreamSynchronize(stream);
+        std::fprintf(stderr, "[ifb fit] alloc+launch %.3f ms, kernel done at %.3f ms (stage=%d small_in_smem=%d dyn=%zu)\n",
+                     t_launch, ms_since(t_start), p.stage, p.small_in_smem, dyn);
+    }
+    // node tables back to the host (one pinned staging block, grown on demand and reused across calls: pageable
+    // D2H of the T x cap tables was a third of a 512-tree fit), then compacted into the persisted layout
+    std::unique_lock<std::mutex> stage_lock(g_stage.mu);
+    const size_t per_node = 4 + 4 + 8 + (ext ? 8 + 4 : 4 + 8);
+    // hyperplane rows of all trees ride in the same batch when they are small enough to stage whole
+    const size_t hp_elems = ext ? T * (size_t)cap_internal * k : 0;
+    const bool hp_staged = ext && hp_elems * 8 <= ((size_t)64 << 20);
+    const size_t stage_bytes = T * 8 + T * (size_t)cap * per_node + (hp_staged ? hp_elems * 8 + 16 : 0) + 64;
+    if ((rc = g_stage.reserve(stage_bytes))) return rc;
+    unsigned char *sp = (unsigned char *)g_stage.p;
+    auto carve = [&](size_t bytes) { void *r = sp; sp += (bytes + 7) & ~(size_t)7; return r; };
+    int64_t *ninst = (int64_t *)carve(T * cap * 8);
+    double *thr = ext ? nullptr : (double *)carve(T * cap * 8);
+    double *off = ext ? (double *)carve(T * cap * 8) : nullptr;
+    int32_t *left = (int32_t *)carve(T * cap * 4), *right = (int32_t *)carve(T * cap * 4);
+    int32_t *feature = ext ? nullptr : (int32_t *)carve(T * cap * 4);
+    int32_t *slot = ext ? (int32_t *)carve(T * cap * 4) : nullptr;
+    int32_t *n_nodes = (int32_t *)carve(T * 4), *n_int = (int32_t *)carve(T * 4);
+    int32_t *hidx_all = hp_staged ? (int32_t *)carve(hp_elems * 4) : nullptr;
+    float *hw_all = hp_staged ? (float *)carve(hp_elems * 4) : nullptr;
+    if (hp_staged && ntrees > 0) {
+        IFB_CUDA(cudaMemcpyAsync(hidx_all, p.hp_idx, hp_elems * 4, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaMemcpyAsync(hw_all, p.hp_w, hp_elems * 4, cudaMemcpyDeviceToHost, stream));
+    }
+    IFB_CUDA(cudaMemcpyAsync(n_nodes, p.n_nodes, T * 4, cudaMemcpyDeviceToHost, stream));
+    IFB_CUDA(cudaMemcpyAsync(left, p.left, T * cap * 4, cudaMemcpyDeviceToHost, stream));
+    IFB_CUDA(cudaMemcpyAsync(right, p.right, T * cap * 4, cudaMemcpyDeviceToHost, stream));
+    IFB_CUDA(cudaMemcpyAsync(ninst, p.num_instances, T * cap * 8, cudaMemcpyDeviceToHost, stream));
     if (ext) {
-        off.resize(T * cap);
-        slot.resize(T * cap);
-        IFB_CUDA(cudaMemcpyAsync(n_int.data(), p.n_internal, T * 4, cudaMemcpyDeviceToHost, stream));
-        IFB_CUDA(cudaMemcpyAsync(off.data(), p.offset, T * cap * 8, cudaMemcpyDeviceToHost, stream));
-        IFB_CUDA(cudaMemcpyAsync(slot.data(), p.hp_slot, T * cap * 4, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaMemcpyAsync(n_int, p.n_internal, T * 4, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaMemcpyAsync(off, p.offset, T * cap * 8, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaMemcpyAsync(slot, p.hp_slot, T * cap * 4, cudaMemcpyDeviceToHost, stream));
     } else {
-        feature.resize(T * cap);
-        thr.resize(T * cap);
-        IFB_CUDA(cudaMemcpyAsync(feature.data(), p.feature, T * cap * 4, cudaMemcpyDeviceToHost, stream));
-        IFB_CUDA(cudaMemcpyAsync(thr.data(), p.threshold, T * cap * 8, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaMemcpyAsync(feature, p.feature, T * cap * 4, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaMemcpyAsync(thr, p.threshold, T * cap * 8, cudaMemcpyDeviceToHost, stream));
     }
     IFB_CUDA(cudaStreamSynchronize(stream));
     std::vector<int32_t> node_off(ntrees + 1, 0);
@@ -698,6 +870,10 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     if (ext) {
         c_off.resize(total);
         hp_off.assign(total + 1, 0);
+        size_t internal_total = 0;
+        for (int t = 0; t < ntrees; t++) internal_total += (size_t)std::max(n_int[t], 0);
+        hp_idx.reserve(internal_total * k);
+        hp_w.reserve(internal_total * k);
     } else {
         c_feat.resize(total);
         c_thr.resize(total);
@@ -716,29 +892,41 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
         } else {
             std::memcpy(&c_off[dst], &off[src], nn * 8);
             const int ni = n_int[t];
-            hidx_t.resize((size_t)ni * k);
-            hw_t.resize((size_t)ni * k);
-            if (ni > 0) {
-                IFB_CUDA(cudaMemcpy(hidx_t.data(), p.hp_idx + (int64_t)t * cap_internal * k, (size_t)ni * k * 4,
-                                    cudaMemcpyDeviceToHost));
-                IFB_CUDA(cudaMemcpy(hw_t.data(), p.hp_w + (int64_t)t * cap_internal * k, (size_t)ni * k * 4,
-                                    cudaMemcpyDeviceToHost));
+            const int32_t *hidx_p;
+            const float *hw_p;
+            if (hp_staged) {
+                hidx_p = hidx_all + (size_t)t * cap_internal * k;
+                hw_p = hw_all + (size_t)t * cap_internal * k;
+            } else {
+                hidx_t.resize((size_t)ni * k);
+                hw_t.resize((size_t)ni * k);
+                if (ni > 0) {
+                    IFB_CUDA(cudaMemcpy(hidx_t.data(), p.hp_idx + (int64_t)t * cap_internal * k, (size_t)ni * k * 4,
+                                        cudaMemcpyDeviceToHost));
+                    IFB_CUDA(cudaMemcpy(hw_t.data(), p.hp_w + (int64_t)t * cap_internal * k, (size_t)ni * k * 4,
+                                        cudaMemcpyDeviceToHost));
+                }
+                hidx_p = hidx_t.data();
+                hw_p = hw_t.data();
             }
             for (int i = 0; i < nn; i++) {
                 const int s = slot[src + i];
                 if (left[src + i] != -1) {
-                    hp_idx.insert(hp_idx.end(), hidx_t.begin() + (size_t)s * k, hidx_t.begin() + (size_t)(s + 1) * k);
-                    hp_w.insert(hp_w.end(), hw_t.begin() + (size_t)s * k, hw_t.begin() + (size_t)(s + 1) * k);
+                    hp_idx.insert(hp_idx.end(), hidx_p + (size_t)s * k, hidx_p + (size_t)(s + 1) * k);
+                    hp_w.insert(hp_w.end(), hw_p + (size_t)s * k, hw_p + (size_t)(s + 1) * k);
                 }
                 hp_off[dst + i + 1] = (int64_t)hp_idx.size();
             }
         }
     }
-    if (ext)
-        return ifb_forest_create_extended(device, ntrees, node_off.data(), c_left.data(), c_right.data(), c_ninst.data(),
-                                          c_off.data(), hp_off.data(), hp_idx.data(), hp_w.data(), n, d, out);
-    return ifb_forest_create_standard(device, ntrees, node_off.data(), c_left.data(), c_right.data(), c_feat.data(),
-                                      c_thr.data(), c_ninst.data(), n, d, out);
+    stage_lock.unlock();
+    if (timing) std::fprintf(stderr, "[ifb fit] tables on the host and compacted at %.3f ms\n", ms_since(t_start));
+    rc = ext ? ifb_forest_create_extended(device, ntrees, node_off.data(), c_left.data(), c_right.data(), c_ninst.data(),
+                                          c_off.data(), hp_off.data(), hp_idx.data(), hp_w.data(), n, d, out)
+             : ifb_forest_create_standard(device, ntrees, node_off.data(), c_left.data(), c_right.data(), c_feat.data(),
+                                          c_thr.data(), c_ninst.data(), n, d, out);
+    if (timing) std::fprintf(stderr, "[ifb fit] forest handle created at %.3f ms\n", ms_since(t_start));
+    return rc;
 }
 
 extern "C" int ifb_fit_host(int32_t device, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,

@@ -195,13 +195,37 @@ int build_extended_tables(ifb_forest *f) {
     f->ext_internal_slots = internal;
     f->ext_dense_identity = identity && internal > 0;
     DeviceGuard dg(f->device);
+    // Every table goes into ONE device allocation (a dozen cudaMallocs cost more than the uploads): `up` records
+    // the request, `commit` allocates the arena, copies each piece and hands out the 256-byte aligned pointers.
+    struct Piece {
+        void **dptr;
+        const void *src;
+        size_t bytes, at;
+    };
+    std::vector<Piece> pieces;
+    size_t arena_bytes = 0;
     auto up = [&](void **dptr, const void *src, size_t bytes) -> int {
         if (bytes == 0) bytes = 16;
-        IFB_CUDA(cudaMalloc(dptr, bytes));
-        if (src) IFB_CUDA(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
-        f->device_bytes += (int64_t)bytes;
+        pieces.push_back(Piece{dptr, src, bytes, arena_bytes});
+        arena_bytes += (bytes + 255) & ~(size_t)255;
         return IFB_OK;
     };
+    auto commit = [&]() -> int {
+        IFB_CUDA(cudaMalloc((void **)&f->d_ext_arena, arena_bytes));
+        f->device_bytes += (int64_t)arena_bytes;
+        for (const Piece &pc : pieces) {
+            *pc.dptr = f->d_ext_arena + pc.at;
+            if (pc.src) IFB_CUDA(cudaMemcpyAsync(*pc.dptr, pc.src, pc.bytes, cudaMemcpyHostToDevice, 0));
+        }
+        IFB_CUDA(cudaStreamSynchronize(0));
+        return IFB_OK;
+    };
+    // host tables referenced by `pieces` must outlive commit()
+    std::vector<double> wabs((size_t)internal, 0.0), wnorm((size_t)internal, 0.0);
+    std::vector<WideNode> wn((size_t)total);
+    std::vector<int32_t> tslot((size_t)std::max(T, 1), -1);
+    std::vector<unsigned char> blob;
+    std::vector<int64_t> boff(T + 1, 0);
     int rc;
     if ((rc = up((void **)&f->d_ext_w, w.data(), w.size() * 4))) return rc;
     if (!f->ext_dense_identity)
@@ -212,7 +236,6 @@ int build_extended_tables(ifb_forest *f) {
     if ((rc = up((void **)&f->d_ext_hp, hp.data(), hp.size() * 4))) return rc;
     if ((rc = up((void **)&f->d_ext_len, len.data(), len.size() * 4))) return rc;
     {
-        std::vector<double> wabs((size_t)internal, 0.0), wnorm((size_t)internal, 0.0);
         for (int64_t sl = 0; sl < internal; sl++) {
             double a = 0.0, q = 0.0;
             for (int i = 0; i < k; i++) {
@@ -225,8 +248,6 @@ int build_extended_tables(ifb_forest *f) {
         }
         if ((rc = up((void **)&f->d_ext_wabs, wabs.data(), wabs.size() * 8))) return rc;
         if ((rc = up((void **)&f->d_ext_wnorm, wnorm.data(), wnorm.size() * 8))) return rc;
-        std::vector<WideNode> wn((size_t)total);
-        std::vector<int32_t> tslot((size_t)std::max(T, 1), -1);
         for (int t = 0; t < T; t++) {
             const int64_t base = f->node_off[t];
             const int n = f->node_off[t + 1] - f->node_off[t];
@@ -264,8 +285,6 @@ int build_extended_tables(ifb_forest *f) {
     if (f->ext_dense_identity && k <= 64) {
         const int D = k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64;
         const int WS = D + 4;  // row stride in floats: 16-byte units odd => per-lane LDS.128 gathers spread over banks
-        std::vector<unsigned char> blob;
-        std::vector<int64_t> boff(T + 1, 0);
         int64_t mx = 0;
         for (int t = 0; t < T; t++) {
             const int64_t base = f->node_off[t];
@@ -314,7 +333,7 @@ int build_extended_tables(ifb_forest *f) {
         if ((rc = up((void **)&f->d_ext_blob, blob.data(), blob.size()))) return rc;
         if ((rc = up((void **)&f->d_ext_blob_off, boff.data(), boff.size() * 8))) return rc;
     }
-    return IFB_OK;
+    return commit();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -487,20 +506,7 @@ ifb_forest::~ifb_forest() {
     cudaFree(d_gfeat);
     cudaFree(d_gchild);
     cudaFree(d_groot);
-    cudaFree(d_ext_w);
-    cudaFree(d_ext_idx);
-    cudaFree(d_ext_off);
-    cudaFree(d_ext_leaf);
-    cudaFree(d_ext_child);
-    cudaFree(d_ext_hp);
-    cudaFree(d_ext_len);
-    cudaFree(d_ext_wabs);
-    cudaFree(d_ext_wnorm);
-    cudaFree(d_ext_wide_nodes);
-    cudaFree(d_ext_tree_slot);
-    cudaFree(d_ext_tree_node);
-    cudaFree(d_ext_blob);
-    cudaFree(d_ext_blob_off);
+    cudaFree(d_ext_arena);   // every d_ext_* table is a slice of it
 }
 
 using namespace ifb;
@@ -572,10 +578,12 @@ static int check_device(int32_t device) {
         return IFB_ENOGPU;
     }
     IFB_REQUIRE(device >= 0 && device < n, "device %d out of range [0,%d)", device, n);
-    cudaDeviceProp prop;
-    IFB_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    // cudaGetDeviceProperties costs about a millisecond per call; two attributes are all that is needed
+    int major = 0, minor = 0;
+    IFB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    IFB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, major, minor);
         return IFB_ENOGPU;
     }
     return IFB_OK;

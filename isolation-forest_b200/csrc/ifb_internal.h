@@ -150,6 +150,7 @@ struct ifb_forest {
     // off[], w[internal][D+4]) that score_ext_dense_kernel streams into shared memory with a bulk async copy
     unsigned char *d_ext_blob = nullptr;
     int64_t *d_ext_blob_off = nullptr;   // [T+1] byte offsets (16-byte aligned)
+    unsigned char *d_ext_arena = nullptr; // the one allocation every d_ext_* table above is a slice of
     int32_t ext_blob_D = 0;              // padded hyperplane width (8/16/32/64), 0 = no blob layout
     int64_t ext_blob_max = 0;            // largest blob in bytes
     bool ext_w_safe = false;             // every hyperplane weight is normal with 2^-60 <= |w| <= 2^40

@@ -58,6 +58,22 @@ def test_extended_fit_bit_identical(nat, oracle, n_rows, d, T, n, nf, ext, seed)
     assert_tables_equal(got, ref)
 
 
+@pytest.mark.parametrize("mode", ["smem", "scratch", "unstaged"])
+def test_sample_staging_modes_build_the_same_trees(nat, oracle, mode, monkeypatch):
+    """The builder stages each tree's sample in shared memory, in an L2-resident scratch when it does not fit,
+    or (IFB_FIT_NO_STAGE test hook / very large samples) reads the training matrix directly: same trees."""
+    d = 300 if mode == "scratch" else 48           # 300 x 256 x 4 B = 307 KB does not fit a CTA's shared memory
+    if mode == "unstaged":
+        monkeypatch.setenv("IFB_FIT_NO_STAGE", "1")
+    X = synth_mixture(6000, d, 77)
+    X[::7, 1] = -2.0
+    for ext in (-1, d - 1, 2):
+        ref = oracle.fit_forest(X, 12, 256, random_seed=21, ext_level=ext)
+        for colmajor in (True, False):
+            got = fit_gpu(nat, X, 12, 256, seed=21, ext=ext, colmajor=colmajor).export()
+            assert_tables_equal(got, ref)
+
+
 def test_identical_rows_and_constant_features(nat, oracle):
     same = np.ones((64, 3), np.float32)
     got = fit_gpu(nat, same, 5, 16, seed=3).export()
