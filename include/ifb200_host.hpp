@@ -37,11 +37,16 @@ struct IFBH_CLASS IllegalStateException : std::logic_error {
 // Feature vectors of a Dataset: `rows` vectors of size `cols`, row-major.  Exactly one of f64 / f32 is set.
 // f64 is what Spark's ml.linalg.Vector holds; the engine casts to f32 (`.toFloat`) like the reference
 // (IF/IsolationForest.scala:54, IF/IsolationForestModel.scala:136).
+// A column of SparseVectors is passed as CSR (indptr[rows + 1], ascending indices per row, f64 values as Spark
+// stores them); absent entries are 0.0, exactly what Vector.apply / toArray give the reference.
 struct FeatureMatrix {
     int64_t rows = 0;
     int32_t cols = 0;
-    const double *f64 = nullptr;
-    const float *f32 = nullptr;
+    const double *f64 = nullptr;          // dense, row-major rows x cols
+    const float *f32 = nullptr;           // dense, row-major rows x cols
+    const int64_t *csr_indptr = nullptr;  // sparse: exactly one of f64 / f32 / csr_indptr is set
+    const int32_t *csr_indices = nullptr;
+    const double *csr_values = nullptr;
 };
 
 struct ScoredData {                      // the two columns transform appends
@@ -221,6 +226,11 @@ IFBH_API int ifbh_model_destroy(void *model);
 IFBH_API int ifbh_model_set(void *model, const char *param, const char *json_value);
 IFBH_API int ifbh_model_transform(void *model, const double *x_f64, const float *x_f32, int64_t rows, int32_t cols,
                                   double *scores, double *predictions);
+// the same two calls for a SparseVector column (CSR: indptr[rows + 1], indices, f64 values)
+IFBH_API int ifbh_estimator_fit_csr(void *est, const int64_t *indptr, const int32_t *indices, const double *values,
+                                    int64_t rows, int32_t cols, void **model_out);
+IFBH_API int ifbh_model_transform_csr(void *model, const int64_t *indptr, const int32_t *indices, const double *values,
+                                      int64_t rows, int32_t cols, double *scores, double *predictions);
 IFBH_API int ifbh_model_save(void *model, const char *path, int overwrite);
 IFBH_API int ifbh_model_load(int extended, const char *path, void **model_out);
 // JSON description: uid, class, paramMap, numSamples, numFeatures, totalNumFeatures, outlierScoreThreshold,

@@ -10,7 +10,7 @@ Names, defaults, argument meaning and error behaviour follow the reference
     ExtendedIsolationForest().setExtensionLevel(5) ...
 
 ``X`` is the featuresCol content: a (rows x features) array of float64 (Spark Vector values; cast to float like
-``.toFloat``) or float32.  `require` failures raise IllegalArgumentException (a ValueError).
+``.toFloat``) or float32, or a scipy CSR matrix for a column of SparseVectors (absent entries are 0.0).  `require` failures raise IllegalArgumentException (a ValueError).
 """
 from __future__ import annotations
 
@@ -53,6 +53,8 @@ def hlib():
         L.ifbh_model_destroy.argtypes = [vp]
         L.ifbh_model_set.argtypes = [vp, cp, cp]
         L.ifbh_model_transform.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
+        L.ifbh_estimator_fit_csr.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int32, C.POINTER(vp)]
+        L.ifbh_model_transform_csr.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
         L.ifbh_model_save.argtypes = [vp, cp, C.c_int]
         L.ifbh_model_load.argtypes = [C.c_int, cp, C.POINTER(vp)]
         L.ifbh_model_describe.argtypes = [vp, vp, C.c_int64]
@@ -84,6 +86,19 @@ def _matrix(X):
         return X, None, C.c_void_p(X.ctypes.data)
     X = np.ascontiguousarray(X, np.float64)
     return X, C.c_void_p(X.ctypes.data), None
+
+
+def _csr(X):
+    """A column of SparseVectors: any object with CSR attributes (scipy.sparse.csr_matrix / csr_array)."""
+    if not (hasattr(X, "indptr") and hasattr(X, "indices") and hasattr(X, "data") and hasattr(X, "shape")):
+        return None
+    indptr = np.ascontiguousarray(X.indptr, np.int64)
+    indices = np.ascontiguousarray(X.indices, np.int32)
+    values = np.ascontiguousarray(X.data, np.float64)
+    n, d = X.shape
+    if len(indptr) != n + 1:
+        raise IllegalArgumentException("sparse features must be in CSR form (one indptr entry per row + 1)")
+    return indptr, indices, values, int(n), int(d)
 
 
 class Scored:
@@ -155,6 +170,15 @@ class _Model(_ParamsMixin):
     def numTrees(self): return self._describe()["numTrees"]
 
     def transform(self, X) -> Scored:
+        sp = _csr(X)
+        if sp is not None:
+            indptr, indices, values, n, d = sp
+            scores = np.empty(n, np.float64)
+            labels = np.empty(n, np.float64)
+            _check(hlib().ifbh_model_transform_csr(self._h, C.c_void_p(indptr.ctypes.data), C.c_void_p(indices.ctypes.data),
+                                                   C.c_void_p(values.ctypes.data), n, d, C.c_void_p(scores.ctypes.data),
+                                                   C.c_void_p(labels.ctypes.data)))
+            return Scored(scores, labels)
         X, p64, p32 = _matrix(X)
         n, d = X.shape
         scores = np.empty(n, np.float64)
@@ -261,9 +285,15 @@ class _Estimator(_ParamsMixin):
         return name in self._set_params
 
     def fit(self, X):
+        out = C.c_void_p()
+        sp = _csr(X)
+        if sp is not None:
+            indptr, indices, values, n, d = sp
+            _check(hlib().ifbh_estimator_fit_csr(self._h, C.c_void_p(indptr.ctypes.data), C.c_void_p(indices.ctypes.data),
+                                                 C.c_void_p(values.ctypes.data), n, d, C.byref(out)))
+            return self._MODEL(out.value)
         X, p64, p32 = _matrix(X)
         n, d = X.shape
-        out = C.c_void_p()
         _check(hlib().ifbh_estimator_fit(self._h, p64, p32, n, d, C.byref(out)))
         return self._MODEL(out.value)
 

@@ -106,6 +106,20 @@ void castRows(const FeatureMatrix &m, int64_t r0, int64_t r1, float *dst) {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, total / (1 << 20)), std::min(32u, hw));
     std::vector<std::thread> th;
+    if (m.csr_indptr) {   // SparseVector rows: zero-fill, then scatter the stored entries (`.toFloat` each)
+        for (int t = 0; t < nt; t++) {
+            const int64_t ra = r0 + (r1 - r0) * t / nt, rb = r0 + (r1 - r0) * (t + 1) / nt;
+            th.emplace_back([=]() {
+                std::memset(dst + (ra - r0) * m.cols, 0, (size_t)(rb - ra) * m.cols * 4);
+                for (int64_t r = ra; r < rb; r++) {
+                    float *row = dst + (r - r0) * m.cols;
+                    for (int64_t e = m.csr_indptr[r]; e < m.csr_indptr[r + 1]; e++) row[m.csr_indices[e]] = (float)m.csr_values[e];
+                }
+            });
+        }
+        for (auto &x : th) x.join();
+        return;
+    }
     for (int t = 0; t < nt; t++) {
         const int64_t a = total * t / nt, b = total * (t + 1) / nt;
         if (m.f32) {
@@ -122,7 +136,22 @@ void castRows(const FeatureMatrix &m, int64_t r0, int64_t r1, float *dst) {
 
 void checkMatrix(const FeatureMatrix &m) {
     require(m.rows >= 0 && m.cols >= 1, "feature matrix must have at least one column");
-    require((m.f64 != nullptr) != (m.f32 != nullptr) || m.rows == 0, "exactly one of f64 / f32 must be given");
+    const int given = (m.f64 != nullptr) + (m.f32 != nullptr) + (m.csr_indptr != nullptr);
+    require(given == 1 || (m.rows == 0 && given == 0), "exactly one of f64 / f32 / csr must be given");
+    if (m.csr_indptr) {
+        require(m.csr_indptr[0] == 0, "csr_indptr[0] must be 0");
+        for (int64_t r = 0; r < m.rows; r++) {
+            const int64_t a = m.csr_indptr[r], b = m.csr_indptr[r + 1];
+            require(b >= a, "csr_indptr must be non-decreasing");
+            require(b == a || (m.csr_indices && m.csr_values), "null csr arrays");
+            for (int64_t e = a; e < b; e++) {
+                // SparseVector invariants: indices in [0, size), strictly increasing
+                require(m.csr_indices[e] >= 0 && m.csr_indices[e] < m.cols,
+                        "sparse index " + std::to_string(m.csr_indices[e]) + " outside [0, " + std::to_string(m.cols) + ")");
+                require(e == a || m.csr_indices[e] > m.csr_indices[e - 1], "sparse indices must be strictly increasing");
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -683,6 +712,15 @@ int ifbh_estimator_fit(void *est, const double *x64, const float *x32, int64_t r
         *model_out = model;
     });
 }
+int ifbh_estimator_fit_csr(void *est, const int64_t *indptr, const int32_t *indices, const double *values, int64_t rows,
+                           int32_t cols, void **model_out) {
+    return guarded([&] {
+        EstBox *b = (EstBox *)est;
+        FeatureMatrix m{rows, cols, nullptr, nullptr, indptr, indices, values};
+        ForestModelBase *model = b->extended ? (ForestModelBase *)b->ext_->fit(m).release() : (ForestModelBase *)b->std_->fit(m).release();
+        *model_out = model;
+    });
+}
 int ifbh_model_create(int extended, const char *uid, int32_t T, const int32_t *node_off, const int32_t *left,
                       const int32_t *right, const int32_t *feature, const double *threshold, const int64_t *ninst,
                       const double *offset, const int64_t *hp_off, const int32_t *hp_idx, const float *hp_w,
@@ -727,6 +765,17 @@ int ifbh_model_transform(void *model, const double *x64, const float *x32, int64
     return guarded([&] {
         ForestModelBase *m = (ForestModelBase *)model;
         ScoredData s = m->transform(FeatureMatrix{rows, cols, x64, x32});
+        if (rows > 0) {
+            std::memcpy(scores, s.outlierScore.data(), (size_t)rows * 8);
+            if (predictions) std::memcpy(predictions, s.predictedLabel.data(), (size_t)rows * 8);
+        }
+    });
+}
+int ifbh_model_transform_csr(void *model, const int64_t *indptr, const int32_t *indices, const double *values,
+                             int64_t rows, int32_t cols, double *scores, double *predictions) {
+    return guarded([&] {
+        ForestModelBase *m = (ForestModelBase *)model;
+        ScoredData s = m->transform(FeatureMatrix{rows, cols, nullptr, nullptr, indptr, indices, values});
         if (rows > 0) {
             std::memcpy(scores, s.outlierScore.data(), (size_t)rows * 8);
             if (predictions) std::memcpy(predictions, s.predictedLabel.data(), (size_t)rows * 8);

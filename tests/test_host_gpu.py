@@ -187,3 +187,27 @@ def test_bootstrap_maxfeatures_and_partitions_reach_the_builder(pkg, oracle, mam
             assert np.array_equal(got[key], ref[key]), (setters, key)
         assert m.getNumSamples() == ns
         assert m.getNumFeatures() == okw.get("num_features", 6)
+
+
+def test_sparse_vector_column_scores_like_its_dense_form(pkg, oracle):
+    """SparseVector rows (CSR ingest): fit and transform give exactly what the densified column gives."""
+    sp = pytest.importorskip("scipy.sparse")
+    rng = np.random.default_rng(5)
+    dense = np.where(rng.random((4000, 12)) < 0.3, rng.standard_normal((4000, 12)), 0.0)
+    dense[::50] = 0.0                                   # all-zero rows
+    X = sp.csr_matrix(dense)
+    E = pkg.estimators
+    est = E.IsolationForest().setNumEstimators(40).setMaxSamples(128).setContamination(0.05).setRandomSeed(3)
+    m_sparse, m_dense = est.fit(X), est.fit(dense)
+    ts, td = m_sparse.tables(), m_dense.tables()
+    for k in ("node_off", "left", "right", "feature", "threshold", "num_instances"):
+        assert np.array_equal(ts[k], td[k]), k
+    assert m_sparse.getOutlierScoreThreshold() == m_dense.getOutlierScoreThreshold()
+    a, b = m_sparse.transform(X), m_dense.transform(dense)
+    assert np.array_equal(a.outlierScore, b.outlierScore) and np.array_equal(a.predictedLabel, b.predictedLabel)
+    ref = oracle.Forest(ts).score(dense.astype(np.float32))
+    np.testing.assert_allclose(a.outlierScore, ref, rtol=1e-12, atol=0)
+    bad = sp.csr_matrix(dense[:10])
+    bad.indices[0] = 99
+    with pytest.raises(E.IllegalArgumentException, match="sparse index 99"):
+        m_sparse.transform(bad)
