@@ -162,3 +162,26 @@ def test_resolved_params_messages(pkg):
         pkg.IsolationForest().setMaxSamples(10).setMaxFeatures(5).fit(X)
     with pytest.raises(pkg.IllegalArgumentException, match=r"extensionLevel given invalid value 4, but must be in \[0, 3\] for a subspace of 4 features"):
         pkg.ExtendedIsolationForest().setMaxSamples(10).setExtensionLevel(4).fit(X)   # extended test :184-211
+
+
+def test_sparse_column_validation_and_no_cpu_fallback(pkg):
+    """SparseVector (CSR) ingest: the SparseVector invariants are checked on the host before any device work, and a
+    valid matrix on a box without a GPU fails loudly instead of being scored by some CPU path."""
+    sp = pytest.importorskip("scipy.sparse")
+    E = pkg.estimators
+    t = dict(num_trees=1, node_off=np.array([0, 3], np.int32), left=np.array([1, -1, -1], np.int32),
+             right=np.array([2, -1, -1], np.int32), feature=np.array([0, -1, -1], np.int32),
+             threshold=np.array([0.5, 0.0, 0.0]), num_instances=np.array([-1, 1, 1], np.int64))
+    m = E.IsolationForestModel.from_tables("uid", t, 2, 3, 3)
+    X = sp.csr_matrix(np.eye(3))
+    X.indices[0] = 7
+    with pytest.raises(E.IllegalArgumentException, match=r"sparse index 7 outside \[0, 3\)"):
+        m.transform(X)
+    X = sp.csr_matrix(np.array([[1.0, 2.0, 0.0], [0.0, 0.0, 3.0]]))
+    X.indices[:2] = [1, 0]
+    with pytest.raises(E.IllegalArgumentException, match="strictly increasing"):
+        m.transform(X)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CUDA device available"):
+            m.transform(sp.csr_matrix(np.eye(3)))
