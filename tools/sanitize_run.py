@@ -12,6 +12,21 @@ rng = np.random.default_rng(0)
 def cm(X):
     return torch.from_numpy(np.ascontiguousarray(X.T)).cuda().t()
 
+if "--fit-only" in sys.argv:   # the tree builder alone (shared-memory staged, scratch staged, extended)
+    for (n, d, T, ext, ns) in ((3000, 32, 6, -1, 256), (1500, 128, 4, -1, 256), (700, 300, 3, -1, 256), (900, 5, 3, -1, 700),
+                               (2000, 64, 3, 63, 256), (1200, 12, 3, 3, 128), (600, 300, 2, 299, 128)):
+        X = rng.standard_normal((n, d)).astype(np.float32)
+        X[::9, 0] = 0.25
+        for colmajor in (True, False):
+            Xd = cm(X) if colmajor else torch.from_numpy(X).cuda()
+            tb = nat.fit_device(Xd, nat.FitParams(T, ns, d, 0, 1, 1, ext, 0, 0)).export()
+            ref = O.fit_forest(X, T, ns, random_seed=1, ext_level=ext)
+            for k in ("node_off", "left", "right", "num_instances"):
+                assert np.array_equal(tb[k], ref[k]), (n, d, T, ext, k)
+        print("fit ok", n, d, T, ext, ns, flush=True)
+    print("sanitize_run (fit only) done")
+    sys.exit(0)
+
 for (n, d, T, ext) in ((3000, 32, 20, -1), (1500, 128, 30, -1), (700, 900, 6, -1), (2500, 8, 10, 7), (2000, 64, 6, 63),
                        (600, 256, 4, 255), (1200, 12, 5, 3)):
     X = rng.standard_normal((n, d)).astype(np.float32)
