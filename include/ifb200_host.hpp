@@ -101,6 +101,8 @@ class IFBH_CLASS ForestParams {
     // generic access by Spark param name (used by the flat C API and by persistence)
     void setByName(const std::string &name, const std::string &json_value);
     std::string paramMapJson(bool extended) const;
+    // Params.isSet(param): explicitly set through a setter (as opposed to carrying its default)
+    bool isSet(const std::string &name) const;
 
    protected:
     std::string owner = "isolation-forest";
@@ -116,6 +118,7 @@ class IFBH_CLASS ForestParams {
     bool extensionLevelSet = false;
     int device = 0;
     int numPartitions = 1;
+    unsigned explicitlySet = 0;   // bit per Spark param, see paramBit() in host/model.cpp
     friend class ForestModelBase;
     friend class ForestEstimatorBase;
 };
@@ -175,6 +178,9 @@ class IFBH_CLASS ExtendedIsolationForestModel final : public ForestModelBase {
 class IFBH_CLASS ForestEstimatorBase : public ForestParams {
    public:
     const std::string &uid() const { return uid_; }
+    // DefaultParamsWritable: estimator.write[.overwrite()].save(path) -> path/metadata/part-00000 holding
+    // {class, timestamp, sparkVersion, uid, paramMap (explicitly set params), defaultParamMap}
+    void save(const std::string &path, bool overwrite = false) const;
 
    protected:
     ForestEstimatorBase(bool extended, std::string uid);
@@ -188,6 +194,7 @@ class IFBH_CLASS IsolationForest final : public ForestEstimatorBase {
     IsolationForest();                           // Identifiable.randomUID("isolation-forest")
     explicit IsolationForest(std::string uid);
     std::unique_ptr<IsolationForestModel> fit(const FeatureMatrix &data) const;   // IF/IsolationForest.scala:46
+    static std::unique_ptr<IsolationForest> load(const std::string &path);       // DefaultParamsReadable, :114
 };
 
 class IFBH_CLASS ExtendedIsolationForest final : public ForestEstimatorBase {
@@ -195,6 +202,7 @@ class IFBH_CLASS ExtendedIsolationForest final : public ForestEstimatorBase {
     ExtendedIsolationForest();                   // randomUID("extended-isolation-forest")
     explicit ExtendedIsolationForest(std::string uid);
     std::unique_ptr<ExtendedIsolationForestModel> fit(const FeatureMatrix &data) const;  // extended/...:40
+    static std::unique_ptr<ExtendedIsolationForest> load(const std::string &path);       // extended/...:125
 };
 
 // resolved numFeatures / numSamples (validateAndResolveParams, IF/core/SharedTrainLogic.scala:27-78)
@@ -214,6 +222,10 @@ IFBH_API const char *ifbh_last_error(void);
 IFBH_API int ifbh_last_error_kind(void);  // 1 IllegalArgumentException, 2 IllegalStateException, 3 other
 IFBH_API int ifbh_estimator_create(int extended, const char *uid_or_null, void **out);
 IFBH_API int ifbh_estimator_destroy(void *est);
+IFBH_API int ifbh_estimator_save(void *est, const char *path, int overwrite);
+IFBH_API int ifbh_estimator_load(int extended, const char *path, void **est_out);
+// JSON {uid, paramMap (every param with a value), set: [names explicitly set]} ; returns the length needed
+IFBH_API int64_t ifbh_estimator_describe(void *est, char *buf, int64_t cap);
 IFBH_API int ifbh_estimator_set(void *est, const char *param, const char *json_value);
 IFBH_API int ifbh_estimator_fit(void *est, const double *x_f64, const float *x_f32, int64_t rows, int32_t cols,
                                 void **model_out);

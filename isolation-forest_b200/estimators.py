@@ -48,6 +48,10 @@ def hlib():
         L.ifbh_estimator_create.argtypes = [C.c_int, cp, C.POINTER(vp)]
         L.ifbh_estimator_destroy.argtypes = [vp]
         L.ifbh_estimator_set.argtypes = [vp, cp, cp]
+        L.ifbh_estimator_save.argtypes = [vp, cp, C.c_int]
+        L.ifbh_estimator_load.argtypes = [C.c_int, cp, C.POINTER(vp)]
+        L.ifbh_estimator_describe.argtypes = [vp, vp, C.c_int64]
+        L.ifbh_estimator_describe.restype = C.c_int64
         L.ifbh_estimator_fit.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, C.POINTER(vp)]
         L.ifbh_model_create.argtypes = [C.c_int, cp, C.c_int32] + [vp] * 10 + [C.c_int32] * 3 + [C.POINTER(vp)]
         L.ifbh_model_destroy.argtypes = [vp]
@@ -264,11 +268,13 @@ class _Estimator(_ParamsMixin):
     _EXTENDED = False
     _MODEL = IsolationForestModel
 
-    def __init__(self, uid: str | None = None):
+    def __init__(self, uid: str | None = None, _handle=None):
+        if _handle is not None:
+            self._h = C.c_void_p(_handle)
+            return
         h = C.c_void_p()
         _check(hlib().ifbh_estimator_create(int(self._EXTENDED), uid.encode() if uid else None, C.byref(h)))
         self._h = h
-        self._set_params = {}
 
     def __del__(self):
         try:
@@ -278,11 +284,49 @@ class _Estimator(_ParamsMixin):
 
     def _set(self, name, value):
         _check(hlib().ifbh_estimator_set(self._h, name.encode(), json.dumps(value).encode()))
-        self._set_params[name] = value
         return self
 
+    def _describe(self):
+        n = hlib().ifbh_estimator_describe(self._h, None, 0)
+        if n < 0:
+            _check(hlib().ifbh_last_error_kind())
+        buf = C.create_string_buffer(n)
+        hlib().ifbh_estimator_describe(self._h, buf, n)
+        return json.loads(buf.value.decode())
+
+    @property
+    def uid(self): return self._describe()["uid"]
+
     def isSet(self, name):
-        return name in self._set_params
+        return name in self._describe()["set"]
+
+    def extractParamMap(self):
+        """Every param that has a value (explicitly set or default), like Params.extractParamMap."""
+        return self._describe()["paramMap"]
+
+    # DefaultParamsWritable / DefaultParamsReadable
+    class _Writer:
+        def __init__(self, est):
+            self._e, self._ow = est, False
+
+        def overwrite(self):
+            self._ow = True
+            return self
+
+        def save(self, path):
+            _check(hlib().ifbh_estimator_save(self._e._h, os.fspath(path).encode(), int(self._ow)))
+
+    def write(self):
+        return _Estimator._Writer(self)
+
+    def save(self, path):
+        self.write().save(path)
+
+    @classmethod
+    def load(cls, path):
+        out = C.c_void_p()
+        _check(hlib().ifbh_estimator_load(int(cls._EXTENDED), os.fspath(path).encode(), C.byref(out)))
+        return cls(_handle=out.value)
 
     def fit(self, X):
         out = C.c_void_p()

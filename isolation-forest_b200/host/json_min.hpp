@@ -278,6 +278,7 @@ inline Value mkDouble(double d) { Value v; v.kind = Value::Double; v.d = d; retu
 inline Value mkBool(bool b) { Value v; v.kind = Value::Bool; v.b = b; return v; }
 inline Value mkString(const std::string &s) { Value v; v.kind = Value::String; v.s = s; return v; }
 inline Value mkObject() { Value v; v.kind = Value::Object; return v; }
+inline Value mkArray() { Value v; v.kind = Value::Array; return v; }
 
 }  // namespace json
 }  // namespace ifb200

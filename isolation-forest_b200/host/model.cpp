@@ -164,47 +164,66 @@ std::string invalid(const std::string &owner, const char *name, const std::strin
 }
 }  // namespace
 
+namespace {
+const char *const kParamNames[] = {"numEstimators", "maxSamples", "contamination", "contaminationError", "maxFeatures", "bootstrap",
+                                   "randomSeed", "featuresCol", "predictionCol", "scoreCol", "extensionLevel"};
+unsigned paramBit(const std::string &name) {
+    for (unsigned i = 0; i < sizeof kParamNames / sizeof *kParamNames; i++)
+        if (name == kParamNames[i]) return 1u << i;
+    return 0;
+}
+}  // namespace
+bool ForestParams::isSet(const std::string &name) const { return (explicitlySet & paramBit(name)) != 0; }
+
 ForestParams &ForestParams::setNumEstimators(int v) {
     require(v > 0, invalid(owner, "numEstimators", std::to_string(v)));
     numEstimators = v;
+    explicitlySet |= paramBit("numEstimators");
     return *this;
 }
 ForestParams &ForestParams::setMaxSamples(double v) {
     require(v > 0.0, invalid(owner, "maxSamples", fmtDouble(v)));
     maxSamples = v;
+    explicitlySet |= paramBit("maxSamples");
     return *this;
 }
 ForestParams &ForestParams::setContamination(double v) {
     require(v >= 0.0 && v < 0.5, invalid(owner, "contamination", fmtDouble(v)));
     contamination = v;
+    explicitlySet |= paramBit("contamination");
     return *this;
 }
 ForestParams &ForestParams::setContaminationError(double v) {
     require(v >= 0.0 && v <= 1.0, invalid(owner, "contaminationError", fmtDouble(v)));
     contaminationError = v;
+    explicitlySet |= paramBit("contaminationError");
     return *this;
 }
 ForestParams &ForestParams::setMaxFeatures(double v) {
     require(v > 0.0, invalid(owner, "maxFeatures", fmtDouble(v)));
     maxFeatures = v;
+    explicitlySet |= paramBit("maxFeatures");
     return *this;
 }
 ForestParams &ForestParams::setBootstrap(bool v) {
     bootstrap = v;
+    explicitlySet |= paramBit("bootstrap");
     return *this;
 }
 ForestParams &ForestParams::setRandomSeed(int64_t v) {
     require(v > 0, invalid(owner, "randomSeed", std::to_string(v)));
     randomSeed = v;
+    explicitlySet |= paramBit("randomSeed");
     return *this;
 }
-ForestParams &ForestParams::setFeaturesCol(const std::string &v) { featuresCol = v; return *this; }
-ForestParams &ForestParams::setPredictionCol(const std::string &v) { predictionCol = v; return *this; }
-ForestParams &ForestParams::setScoreCol(const std::string &v) { scoreCol = v; return *this; }
+ForestParams &ForestParams::setFeaturesCol(const std::string &v) { featuresCol = v; explicitlySet |= paramBit("featuresCol"); return *this; }
+ForestParams &ForestParams::setPredictionCol(const std::string &v) { predictionCol = v; explicitlySet |= paramBit("predictionCol"); return *this; }
+ForestParams &ForestParams::setScoreCol(const std::string &v) { scoreCol = v; explicitlySet |= paramBit("scoreCol"); return *this; }
 ForestParams &ForestParams::setExtensionLevel(int v) {
     require(v >= 0, invalid(owner, "extensionLevel", std::to_string(v)));
     extensionLevel = v;
     extensionLevelSet = true;
+    explicitlySet |= paramBit("extensionLevel");
     return *this;
 }
 int ForestParams::getExtensionLevel() const {
@@ -630,6 +649,69 @@ std::unique_ptr<IsolationForestModel> IsolationForest::fit(const FeatureMatrix &
 }
 ExtendedIsolationForest::ExtendedIsolationForest() : ForestEstimatorBase(true, randomUID("extended-isolation-forest")) {}
 ExtendedIsolationForest::ExtendedIsolationForest(std::string uid) : ForestEstimatorBase(true, std::move(uid)) {}
+
+// ---- estimator persistence: Spark's DefaultParamsWriter / DefaultParamsReader layout ------------------
+// (IF/IsolationForest.scala:25-28,114; IF/extended/ExtendedIsolationForest.scala:23-26,125)
+namespace {
+const char *kStdEstimatorClass = "com.linkedin.relevance.isolationforest.IsolationForest";
+const char *kExtEstimatorClass = "com.linkedin.relevance.isolationforest.extended.ExtendedIsolationForest";
+}  // namespace
+
+void ForestEstimatorBase::save(const std::string &path, bool overwrite) const {
+    namespace fs = std::filesystem;
+    if (fs::exists(path)) {
+        if (!overwrite)
+            throw std::runtime_error("Path " + path + " already exists. To overwrite it, please use write.overwrite().save(path) for Scala and use write().overwrite().save(path) for Java and Python.");
+        fs::remove_all(path);
+    }
+    fs::create_directories(fs::path(path) / "metadata");
+    // paramMap holds the explicitly set params, defaultParamMap the defaults (a fresh instance of the same class)
+    const json::Value all = json::parse(paramMapJson(extended_));
+    const ForestEstimatorBase fresh(extended_, uid_);
+    const json::Value defaults = json::parse(fresh.paramMapJson(extended_));
+    json::Value setMap = json::mkObject();
+    for (auto &kv : all.obj)
+        if (isSet(kv.first)) setMap.obj.push_back(kv);
+    json::Value meta = json::mkObject();
+    meta.obj.emplace_back("class", json::mkString(extended_ ? kExtEstimatorClass : kStdEstimatorClass));
+    meta.obj.emplace_back("timestamp", json::mkInt((long long)std::chrono::duration_cast<std::chrono::milliseconds>(
+                                                        std::chrono::system_clock::now().time_since_epoch()).count()));
+    meta.obj.emplace_back("sparkVersion", json::mkString("3.5.5"));
+    meta.obj.emplace_back("uid", json::mkString(uid_));
+    meta.obj.emplace_back("paramMap", setMap);
+    meta.obj.emplace_back("defaultParamMap", defaults);
+    {
+        std::ofstream o(fs::path(path) / "metadata" / "part-00000");
+        o << json::render(meta) << "\n";
+    }
+    std::ofstream(fs::path(path) / "metadata" / "_SUCCESS").close();
+}
+
+namespace {
+template <typename E>
+std::unique_ptr<E> loadEstimator(const std::string &path, bool extended) {
+    LoadedMeta m = loadMetadata(path, extended ? kExtEstimatorClass : kStdEstimatorClass);
+    auto est = std::make_unique<E>(m.uid);
+    // DefaultParamsReader.getAndSetParams: paramMap entries are `set`; defaultParamMap entries only have to exist
+    // as params of the class (their values are the class's own defaults)
+    if (const json::Value *dm = m.js.get("defaultParamMap"))
+        for (auto &kv : dm->obj)
+            if (!paramBit(kv.first) || (kv.first == "extensionLevel" && !extended))
+                throw IllegalArgumentException("Param " + kv.first + " does not exist.");
+    if (const json::Value *pm = m.js.get("paramMap"))
+        for (auto &kv : pm->obj) {
+            if (kv.first == "extensionLevel" && !extended) throw IllegalArgumentException("Param extensionLevel does not exist.");
+            est->setByName(kv.first, json::render(kv.second));
+        }
+    return est;
+}
+}  // namespace
+std::unique_ptr<IsolationForest> IsolationForest::load(const std::string &path) {
+    return loadEstimator<IsolationForest>(path, false);
+}
+std::unique_ptr<ExtendedIsolationForest> ExtendedIsolationForest::load(const std::string &path) {
+    return loadEstimator<ExtendedIsolationForest>(path, true);
+}
 std::unique_ptr<ExtendedIsolationForestModel> ExtendedIsolationForest::fit(const FeatureMatrix &data) const {
     std::unique_ptr<ForestModelBase> m = fitImpl(data);
     return std::unique_ptr<ExtendedIsolationForestModel>(static_cast<ExtendedIsolationForestModel *>(m.release()));
@@ -703,6 +785,39 @@ int ifbh_estimator_set(void *est, const char *param, const char *json_value) {
         if (!b->extended && std::string(param) == "extensionLevel") throw IllegalArgumentException("Param extensionLevel does not exist.");
         b->params().setByName(param, json_value);
     });
+}
+int ifbh_estimator_save(void *est, const char *path, int overwrite) {
+    return guarded([&] {
+        EstBox *b = (EstBox *)est;
+        if (b->extended) b->ext_->save(path, overwrite != 0);
+        else b->std_->save(path, overwrite != 0);
+    });
+}
+int ifbh_estimator_load(int extended, const char *path, void **est_out) {
+    return guarded([&] {
+        auto b = std::make_unique<EstBox>();
+        b->extended = extended != 0;
+        if (b->extended) b->ext_ = ExtendedIsolationForest::load(path);
+        else b->std_ = IsolationForest::load(path);
+        *est_out = b.release();
+    });
+}
+int64_t ifbh_estimator_describe(void *est, char *buf, int64_t cap) {
+    int64_t n = -1;
+    guarded([&] {
+        EstBox *b = (EstBox *)est;
+        ForestParams &p = b->params();
+        json::Value d = json::mkObject();
+        d.obj.emplace_back("uid", json::mkString(b->extended ? b->ext_->uid() : b->std_->uid()));
+        json::Value pm = json::parse(p.paramMapJson(b->extended));
+        json::Value set = json::mkArray();
+        for (auto &kv : pm.obj)
+            if (p.isSet(kv.first)) set.arr.push_back(json::mkString(kv.first));
+        d.obj.emplace_back("paramMap", pm);
+        d.obj.emplace_back("set", set);
+        n = copyOut(json::render(d), buf, cap);
+    });
+    return n;
 }
 int ifbh_estimator_fit(void *est, const double *x64, const float *x32, int64_t rows, int32_t cols, void **model_out) {
     return guarded([&] {

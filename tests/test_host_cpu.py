@@ -185,3 +185,49 @@ def test_sparse_column_validation_and_no_cpu_fallback(pkg):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CUDA device available"):
             m.transform(sp.csr_matrix(np.eye(3)))
+
+
+def test_estimator_write_read(pkg, tmp_path):
+    """isolationForestEstimatorWriteReadTest (IFT/IsolationForestTest.scala:16-45) and its extended twin: the estimator's
+    params survive write.overwrite().save / load; set and default params stay told apart (DefaultParamsWriter layout)."""
+    E = pkg.estimators
+    contamination = 0.02
+    est1 = (E.IsolationForest().setNumEstimators(200).setBootstrap(True).setMaxSamples(10000).setMaxFeatures(0.7)
+            .setFeaturesCol("featuresTestColumn").setPredictionCol("predictedLabelTestColumn")
+            .setScoreCol("outlierScoreTestColumn").setContamination(contamination)
+            .setContaminationError(contamination * 0.01).setRandomSeed(1))
+    path = tmp_path / "isolationForestEstimatorWriteReadTest"
+    est1.write().overwrite().save(path)
+    with pytest.raises(RuntimeError, match="already exists"):
+        est1.save(path)
+    est2 = E.IsolationForest.load(path)
+    assert est1.extractParamMap() == est2.extractParamMap()
+    assert est2.uid == est1.uid and est2.isSet("maxFeatures") and est2.isSet("randomSeed")
+    meta = json.loads((path / "metadata" / "part-00000").read_text())
+    assert meta["class"] == "com.linkedin.relevance.isolationforest.IsolationForest"
+    assert meta["paramMap"]["maxSamples"] == 10000.0 and meta["paramMap"]["bootstrap"] is True
+    assert meta["defaultParamMap"]["numEstimators"] == 100 and "extensionLevel" not in meta["defaultParamMap"]
+    assert (path / "metadata" / "_SUCCESS").exists()
+
+    # only what was set lands in paramMap; defaults are restored as defaults
+    d = tmp_path / "defaults"
+    E.IsolationForest().setNumEstimators(7).save(d)
+    meta = json.loads((d / "metadata" / "part-00000").read_text())
+    assert meta["paramMap"] == {"numEstimators": 7}
+    back = E.IsolationForest.load(d)
+    assert back.isSet("numEstimators") and not back.isSet("maxSamples")
+    assert back.extractParamMap()["maxSamples"] == 256.0
+
+    # extended estimator: extensionLevel travels only when set; class names are checked on load
+    x = tmp_path / "ext"
+    ex1 = E.ExtendedIsolationForest().setExtensionLevel(3).setNumEstimators(50)
+    ex1.save(x)
+    ex2 = E.ExtendedIsolationForest.load(x)
+    assert ex2.extractParamMap() == ex1.extractParamMap() and ex2.extractParamMap()["extensionLevel"] == 3
+    y = tmp_path / "ext_default"
+    E.ExtendedIsolationForest().save(y)
+    assert "extensionLevel" not in E.ExtendedIsolationForest.load(y).extractParamMap()
+    with pytest.raises(E.IllegalArgumentException, match="Expected class"):
+        E.IsolationForest.load(x)
+    with pytest.raises(E.IllegalArgumentException, match="Expected class"):
+        E.ExtendedIsolationForestModel.load(x)
