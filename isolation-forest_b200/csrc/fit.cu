@@ -797,6 +797,13 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
             p.sample = b_sample.as<float>();
         }
     }
+    if (const char *force = std::getenv("IFB_FIT_STAGE")) {   // diagnostic: force the L2-scratch staging
+        if (std::atoi(force) == 2 && p.stage == 1 && T * sample_bytes <= kScratchMax) {
+            p.stage = 2;
+            if ((rc = b_sample.alloc(T * sample_bytes))) return rc;
+            p.sample = b_sample.as<float>();
+        }
+    }
     const size_t dyn = p.small_in_smem ? small_aligned + (p.stage == 1 ? sample_bytes : 0) : 0;
     if (ntrees > 0) {
         if (ext) {
