@@ -797,8 +797,17 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
             p.sample = b_sample.as<float>();
         }
     }
-    if (const char *force = std::getenv("IFB_FIT_STAGE")) {   // diagnostic: force the L2-scratch staging
-        if (std::atoi(force) == 2 && p.stage == 1 && T * sample_bytes <= kScratchMax) {
+    // The builder is barrier-latency bound (profiles/r01_fit_kernel_ncu.md: 25 stall cycles per issue on
+    // __syncthreads, 5 % issue utilisation), so what matters is how many trees are in flight.  A shared-memory sample
+    // of 100+ KB leaves one CTA per SM; when that would take more than one wave, stage in the L2 scratch instead (20 KB
+    // of shared memory per CTA, every tree resident at once): 512 trees, d = 128: 5.7 -> 2.4 ms.
+    if (p.stage == 1 && T * sample_bytes <= kScratchMax) {
+        const size_t per_cta = small_aligned + sample_bytes + 3072;          // + static Shared + the 1 KB reserve
+        const size_t ctas_per_sm = std::max<size_t>(1, ((size_t)228 << 10) / per_cta);
+        const bool one_wave = (size_t)ntrees <= ctas_per_sm * (size_t)device_sm_count(device);
+        const char *force = std::getenv("IFB_FIT_STAGE");                    // test hook: 1 / 2 pins the choice
+        const bool to_scratch = force ? std::atoi(force) == 2 : !one_wave;
+        if (to_scratch) {
             p.stage = 2;
             if ((rc = b_sample.alloc(T * sample_bytes))) return rc;
             p.sample = b_sample.as<float>();
