@@ -130,6 +130,24 @@ class _ParamsMixin:
     def setFeaturesCol(self, v): return self._set("featuresCol", str(v))
     def setPredictionCol(self, v): return self._set("predictionCol", str(v))
     def setScoreCol(self, v): return self._set("scoreCol", str(v))
+    # getters of IsolationForestParamsBase (values come from the native param map: set or default)
+    def getNumEstimators(self): return self.extractParamMap()["numEstimators"]
+    def getMaxSamples(self): return self.extractParamMap()["maxSamples"]
+    def getContamination(self): return self.extractParamMap()["contamination"]
+    def getContaminationError(self): return self.extractParamMap()["contaminationError"]
+    def getMaxFeatures(self): return self.extractParamMap()["maxFeatures"]
+    def getBootstrap(self): return self.extractParamMap()["bootstrap"]
+    def getRandomSeed(self): return self.extractParamMap()["randomSeed"]
+    def getFeaturesCol(self): return self.extractParamMap()["featuresCol"]
+    def getPredictionCol(self): return self.extractParamMap()["predictionCol"]
+    def getScoreCol(self): return self.extractParamMap()["scoreCol"]
+
+    def getExtensionLevel(self):
+        pm = self.extractParamMap()
+        if "extensionLevel" not in pm:   # Params.getOrDefault on a param without default: NoSuchElementException
+            raise IllegalStateException("Failed to find a default value for extensionLevel")
+        return pm["extensionLevel"]
+
     # engine parameters without a reference counterpart
     def setDevice(self, v): return self._set("device", int(v))
     def setNumPartitions(self, v): return self._set("numPartitions", int(v))
@@ -167,9 +185,6 @@ class _Model(_ParamsMixin):
     def getOutlierScoreThreshold(self): return self._describe()["outlierScoreThreshold"]
     def setOutlierScoreThreshold(self, v): return self._set("outlierScoreThreshold", float(v))
     def extractParamMap(self): return self._describe()["paramMap"]
-    def getNumEstimators(self): return self.extractParamMap()["numEstimators"]
-    def getContamination(self): return self.extractParamMap()["contamination"]
-    def getExtensionLevel(self): return self.extractParamMap()["extensionLevel"]
     @property
     def numTrees(self): return self._describe()["numTrees"]
 

@@ -218,6 +218,13 @@ def test_estimator_write_read(pkg, tmp_path):
     assert back.isSet("numEstimators") and not back.isSet("maxSamples")
     assert back.extractParamMap()["maxSamples"] == 256.0
 
+    assert (est2.getNumEstimators(), est2.getBootstrap(), est2.getMaxSamples(), est2.getMaxFeatures()) == (200, True, 10000.0, 0.7)
+    assert (est2.getFeaturesCol(), est2.getPredictionCol(), est2.getScoreCol()) == (
+        "featuresTestColumn", "predictedLabelTestColumn", "outlierScoreTestColumn")
+    assert est2.getContamination() == contamination and est2.getRandomSeed() == 1
+    with pytest.raises(E.IllegalStateException, match="extensionLevel"):
+        E.ExtendedIsolationForest().getExtensionLevel()
+
     # extended estimator: extensionLevel travels only when set; class names are checked on load
     x = tmp_path / "ext"
     ex1 = E.ExtendedIsolationForest().setExtensionLevel(3).setNumEstimators(50)
