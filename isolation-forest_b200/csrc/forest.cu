@@ -457,7 +457,7 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
         const StdChunk &c = p->chunks[ci];
         std_fill_top_table(p->h_top.data() + ci * std_top_table_bytes(), val.data() + c.node_begin,
                            meta.data() + c.node_begin, roots.data() + c.tree_begin, c.tree_end - c.tree_begin,
-                           R < 256 ? R : 256);
+                           std_rows_per_box(R, S));
     }
     p->total_words = (int64_t)val.size();
     DeviceGuard dg(f->device);

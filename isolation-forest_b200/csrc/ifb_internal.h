@@ -183,6 +183,7 @@ struct ScatterTarget {
 // score_std.cu
 size_t std_top_table_bytes();
 int std_top_table_max_trees();
+int std_rows_per_box(int rows_per_tile, int stages);   // rows per TMA box / shared-memory sub-tile of a plan
 void std_fill_top_table(void *dst, const float *val, const uint32_t *meta, const uint32_t *root_byte, int n_trees,
                         int rows_per_box);
 int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const float *X, int64_t n_rows,

@@ -26,6 +26,22 @@
 
 namespace ifb {
 
+// Rows per TMA box (== row stride of a shared-memory sub-tile): 256, or the whole tile when it is narrower.
+// Single-stage tiles wider than one box are split into row GROUPS of 256 threads that load, wait and refill
+// independently (see kGroupPipe in the kernel): 1024 -> 4 x 256, 512 -> 2 x 256.  Splitting 256-row tiles into
+// 2 x 128 was measured and LOSES 17 % (d = 128: 128-row boxes halve the contiguous run of every TMA row), so tiles of
+// <= 256 rows keep one box and whole-tile refills.  IFB_STD_NO_GROUPS=1 (A/B hook) restores whole-tile refills.
+bool std_grouped() {
+    static const bool v = getenv("IFB_STD_NO_GROUPS") == nullptr;
+    return v;
+}
+__host__ __device__ constexpr int std_rows_per_box_c(int R, int stages, bool grouped) {
+    (void)stages;
+    (void)grouped;
+    return R < 256 ? R : 256;
+}
+int std_rows_per_box(int R, int stages) { return std_rows_per_box_c(R, stages, std_grouped()); }
+
 namespace {
 
 constexpr int kMaxStages = 2;
@@ -146,12 +162,17 @@ __device__ __forceinline__ uint32_t walk_step(uint32_t node, uint32_t val_s, uin
     return next;
 }
 
-template <int R, int C, bool USE_TMA, bool WANT_DEPTH, int DEEP, int kStages>
+template <int R, int C, bool USE_TMA, bool WANT_DEPTH, int DEEP, int kStages, bool GROUPED>
 __global__ void __launch_bounds__(R, 1)
 score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_rem,
                  const __grid_constant__ TopTable top, const ScoreStdParams p) {
-    constexpr int RB = R < 256 ? R : 256;  // rows per TMA box == row stride of the smem tile
+    constexpr int RB = std_rows_per_box_c(R, kStages, GROUPED);  // rows per TMA box == row stride of the smem tile
     constexpr int NSUB = R / RB;
+    // Group pipelining (single-stage TMA tiles): every row group of RB threads owns its sub-tile, its mbarrier and a
+    // named barrier; a group refills its sub-tile the moment ITS rows are done, so the groups drift out of phase and
+    // one group's TMA fill hides behind the other groups' walks -- double buffering without a second buffer.
+    constexpr bool kGroupPipe = GROUPED && USE_TMA && kStages == 1 && NSUB > 1;
+    constexpr int NBARS = kGroupPipe ? NSUB : kStages;
     constexpr uint32_t COL_BYTES = RB * 4;
     extern __shared__ __align__(1024) unsigned char smem[];
     const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, p.d, kStages);
@@ -163,7 +184,7 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
 
     // ---- one-time setup: barriers, forest chunk, NaN pseudo columns -------------------------------
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < NBARS; s++) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -214,9 +235,21 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
         }
     };
 
+    auto issue_group = [&](int64_t tile, int sub) {
+        // called by the first thread of row group `sub` (kGroupPipe): refill this group's sub-tile only
+        float *sdst = reinterpret_cast<float *>(smem + L.tiles) + (uint32_t)sub * sub_floats;
+        mbar_expect_tx(&bars[sub], (uint32_t)RB * (uint32_t)d * 4u);
+        const int32_t r0 = (int32_t)(tile * R + (int64_t)sub * RB);
+        int f = 0;
+        for (; f + p.box_d <= d; f += p.box_d) tma_load_2d(sdst + (uint32_t)f * RB, &tmap_main, r0, f, &bars[sub]);
+        if (p.rem_d) tma_load_2d(sdst + (uint32_t)f * RB, &tmap_rem, r0, f, &bars[sub]);
+    };
+
     int64_t tile = blockIdx.x;
     const int64_t stride = gridDim.x;
-    if constexpr (USE_TMA) {
+    if constexpr (kGroupPipe) {
+        if (tid % RB == 0 && tile < p.n_tiles) issue_group(tile, tid / RB);
+    } else if constexpr (USE_TMA) {
         if (tid == 0) {
             if (tile < p.n_tiles) issue_tile(tile, 0);
             if (kStages > 1 && tile + stride < p.n_tiles) issue_tile(tile + stride, 1);
@@ -233,7 +266,9 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
 
     for (int64_t k = 0; tile < p.n_tiles; tile += stride, ++k) {
         const int stage = kStages > 1 ? (int)(k & 1) : 0;
-        if constexpr (USE_TMA) {
+        if constexpr (kGroupPipe) {
+            mbar_wait(&bars[sub], (uint32_t)(k & 1));
+        } else if constexpr (USE_TMA) {
             mbar_wait(&bars[stage], kStages > 1 ? (uint32_t)((k >> 1) & 1) : (uint32_t)(k & 1));
         } else {
             load_tile_plain(tile, stage);
@@ -319,9 +354,15 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
             }
             if (WANT_DEPTH) p.depth_sum[row] = dsum;
         }
-        __syncthreads();  // every read of this stage is done before it is refilled
-        if constexpr (USE_TMA) {
-            if (tid == 0 && tile + kStages * stride < p.n_tiles) issue_tile(tile + kStages * stride, stage);
+        if constexpr (kGroupPipe) {
+            // every read of THIS GROUP's sub-tile is done before it is refilled; other groups are not waited for
+            asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "n"(RB) : "memory");
+            if (rl == 0 && tile + stride < p.n_tiles) issue_group(tile + stride, sub);
+        } else {
+            __syncthreads();  // every read of this stage is done before it is refilled
+            if constexpr (USE_TMA) {
+                if (tid == 0 && tile + kStages * stride < p.n_tiles) issue_tile(tile + kStages * stride, stage);
+            }
         }
     }
 }
@@ -376,10 +417,19 @@ int launch_variant(bool use_tma, bool want_depth, const CUtensorMap &m0, const C
         return IFB_OK;
     };
     const bool deep6 = p.max_depth == 8 && !want_depth && use_tma;
-    if (deep6) return go(score_std_kernel<R, C, true, false, 6, S>);
-    if (use_tma)
-        return want_depth ? go(score_std_kernel<R, C, true, true, -1, S>) : go(score_std_kernel<R, C, true, false, -1, S>);
-    return want_depth ? go(score_std_kernel<R, C, false, true, -1, S>) : go(score_std_kernel<R, C, false, false, -1, S>);
+    auto pick = [&](auto g_tag) -> int {
+        constexpr bool G = decltype(g_tag)::value;
+        if (deep6) return go(score_std_kernel<R, C, true, false, 6, S, G>);
+        if (use_tma)
+            return want_depth ? go(score_std_kernel<R, C, true, true, -1, S, G>)
+                              : go(score_std_kernel<R, C, true, false, -1, S, G>);
+        return want_depth ? go(score_std_kernel<R, C, false, true, -1, S, G>)
+                          : go(score_std_kernel<R, C, false, false, -1, S, G>);
+    };
+    if constexpr (S == 1) {
+        if (std_grouped()) return pick(std::true_type{});
+    }
+    return pick(std::false_type{});
 }
 
 }  // namespace
@@ -465,7 +515,7 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
     IFB_REQUIRE(layout == IFB_COL_MAJOR, "launch_score_standard expects a column-major matrix");
     if (n_rows == 0) return IFB_OK;
     const int R = plan->rows_per_tile;
-    const int RB = R < 256 ? R : 256;
+    const int RB = std_rows_per_box(R, plan->stages);
     const bool want_depth = depth_sum != nullptr;
     const size_t n_chunks = plan->chunks.size();
     IFB_REQUIRE(n_chunks <= 1 || path_sum != nullptr || accumulate_only,
