@@ -238,3 +238,22 @@ def test_estimator_write_read(pkg, tmp_path):
         E.IsolationForest.load(x)
     with pytest.raises(E.IllegalArgumentException, match="Expected class"):
         E.ExtendedIsolationForestModel.load(x)
+
+
+def test_cpp_host_params_program(pkg, tmp_path):
+    """The C++ classes used directly, CPU-only part: tests/cpp/host_params.cpp (params, estimator persistence,
+    resolve messages, empty model, a reference-written model when /root/reference is mounted)."""
+    import subprocess
+
+    lib = os.path.join(ROOT, "isolation-forest_b200")
+    exe = tmp_path / "host_params"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "host_params.cpp"), "-o", str(exe), "-L" + lib,
+                           "-lifb200_host", "-lifb200", "-Wl,-rpath," + lib])
+    args = [str(exe), str(tmp_path / "out")]
+    ref_model = os.path.join(IFR, "savedIsolationForestModel")
+    if os.path.isdir(ref_model):
+        args.append(ref_model)
+    out = subprocess.run(args, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "host_params ok" in out.stdout
