@@ -10,8 +10,10 @@
 // reference's order: node by node in PRE-ORDER (the recursion order of the Scala code), so the node tables
 // come out in the persisted pre-order layout.  All data-parallel work of a node (feature min/max, the
 // hyperplane dot products, the partition of the node's row list) is spread over the CTA's threads with
-// warp-shuffle reductions and ballot/popc scans.  This translation unit is compiled with -fmad=false:
-// the JVM never contracts a*b+c, so neither may the f64 split arithmetic here.
+// warp-shuffle reductions and ballot/popc scans.  The tree's sampled rows are staged once, feature-major, in
+// shared memory or an L2-resident scratch (SampleView), and nodes with at most one row replay the feature
+// draws on thread 0 alone instead of running numFeatures block-wide min/max rounds.  This translation unit is
+// compiled with -fmad=false: the JVM never contracts a*b+c, so neither may the f64 split arithmetic here.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>

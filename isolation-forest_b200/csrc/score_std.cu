@@ -7,9 +7,13 @@
 //   * persistent grid, one CTA per SM, R threads; thread r owns row r of the current row tile;
 //   * the node tables of one forest chunk (val[] / meta[] words, see ifb_internal.h) are copied into
 //     shared memory once per CTA;
-//   * row tiles stream through a 2-stage shared-memory ring filled by TMA (cp.async.bulk.tensor.2d on a
-//     tensor map over the column-major matrix; box = RB rows x <=256 features, landing as [feature][RB] so
-//     that lane r reads bank r%32 whatever feature its node asks for) and signalled through mbarriers;
+//   * row tiles are filled by TMA (cp.async.bulk.tensor.2d on a tensor map over the column-major matrix;
+//     box = RB rows x <=256 features, landing as [feature][RB] so that lane r reads bank r%32 whatever
+//     feature its node asks for) and signalled through mbarriers.  Wide single-stage tiles (512 / 1024 rows)
+//     are split into 256-row groups that wait, walk and re-arm their own sub-tile independently, so one
+//     group's fill overlaps the other groups' walks; narrow tiles use a 2-stage ring or whole-tile refills
+//     (the planner in forest.cu picks tile width and depth);
+//   * levels 0 and 1 of every tree come from a kernel-parameter table (constant bank, warp-uniform);
 //   * a walk is a fixed number of steps (the forest's max depth); leaves map onto themselves through the
 //     NaN pseudo feature, so there is no per-level branch; C trees are walked at once per thread for ILP;
 //   * per-row path lengths are added in tree order in f32 (Array[Float].sum), then
