@@ -462,7 +462,9 @@ LoadedMeta loadMetadata(const std::string &path, const std::string &expectedClas
     const json::Value *cls = m.js.get("class");
     require(cls && cls->kind == json::Value::String, "metadata has no class");
     require(cls->s == expectedClass, "Expected class " + expectedClass + ", but found " + cls->s);  // parseMetadata
-    m.uid = m.js.get("uid")->s;
+    const json::Value *uid = m.js.get("uid");
+    require(uid && uid->kind == json::Value::String, "metadata has no uid");
+    m.uid = uid->s;
     return m;
 }
 }  // namespace

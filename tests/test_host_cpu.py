@@ -257,3 +257,17 @@ def test_cpp_host_params_program(pkg, tmp_path):
     out = subprocess.run(args, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "host_params ok" in out.stdout
+
+
+def test_malformed_metadata_is_an_error_not_a_crash(pkg, tmp_path):
+    E = pkg.estimators
+    for body in ('{"class": "com.linkedin.relevance.isolationforest.IsolationForest"}', '{"uid": "x"}', "not json", ""):
+        p = tmp_path / f"bad{abs(hash(body))}"
+        (p / "metadata").mkdir(parents=True)
+        (p / "metadata" / "part-00000").write_text(body + "\n")
+        with pytest.raises((E.IllegalArgumentException, RuntimeError)):
+            E.IsolationForest.load(p)
+        with pytest.raises((E.IllegalArgumentException, RuntimeError)):
+            E.IsolationForestModel.load(p)
+    with pytest.raises(RuntimeError, match="does not exist"):
+        E.IsolationForest.load(tmp_path / "nowhere")
