@@ -197,10 +197,15 @@ Dyn decode(const json::Value &schema, Reader &r) {
         const json::Value *fs = sch->get("fields");
         if (!fs) throw std::runtime_error("avro: record without fields");
         out.null = false;
-        for (auto &f : fs->arr) out.fields.emplace_back(f.get("name")->s, decode(*f.get("type"), r));
+        for (auto &f : fs->arr) {
+            const json::Value *fname = f.get("name"), *ftype = f.get("type");
+            if (!fname || fname->kind != json::Value::String || !ftype) throw std::runtime_error("avro: malformed record field");
+            out.fields.emplace_back(fname->s, decode(*ftype, r));
+        }
     } else if (t == "array") {
         out.null = false;
         const json::Value *it = sch->get("items");
+        if (!it) throw std::runtime_error("avro: array without items");
         while (true) {
             int64_t cnt = r.zz();
             if (cnt == 0) break;
