@@ -45,6 +45,13 @@ TRAIN_ROWS = 1 << 20   # rows of the (rank-independent) training matrix the fore
 FALLBACK_HBM_GBS = 6650.0
 
 
+def workload_label(wl_name, n, d, T, ns, ext):
+    """config.workload, identical for the native and the reference arm."""
+    return (f"{wl_name}: " + ("IsolationForest.fit + " if wl_name in FIT_IN_STEP else "") +
+            f"IsolationForestModel.transform {n}x{d} f32 per GPU, {T} trees, maxSamples={ns}" +
+            (f", extensionLevel={ext}" if ext >= 0 else ""))
+
+
 def mixture_torch(torch, n, d, seed, device):
     """BASELINE's synthetic Gaussian mixture, generated on the device as a column-major (n x d) view."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -178,10 +185,9 @@ def run_reference(args, wl_name, wl):
         "impl": "reference", "metric": "rows scored/sec", "value": value, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 features / f64 thresholds+scores", "data": "synthetic",
-        "config": {"workload": f"{wl_name}: IsolationForestModel.transform {n}x{d} f32, {T} trees, maxSamples={ns}"
-                               + (f", extensionLevel={ext}" if ext >= 0 else ""),
+        "config": {"workload": workload_label(wl_name, n, d, T, ns, ext),
                    "note": "no JVM/Spark in this image: C port of the reference algorithm (oracle/ifb_oracle.c), "
-                           "pthreads over all host cores, bounded sample per step"},
+                           "pthreads over all host cores, bounded sample per step (transform only)"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port",
                          "sample": f"{rows} rows x {d} features per step", "cores_note": cores_note},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -332,9 +338,7 @@ def run_native(args, wl_name, wl):
         "scaling": "strong" if tree_sharded else "weak", "vs_baseline": None,
         "dtype": "f32 features, f32 path sums, f64 scores" + (", f64 hyperplane dots" if ext >= 0 else ""),
         "data": "synthetic",
-        "config": {"workload": f"{wl_name}: " + ("IsolationForest.fit + " if fit_in_step else "") +
-                               f"IsolationForestModel.transform {n}x{d} f32 per GPU, {T} trees, "
-                               f"maxSamples={ns}" + (f", extensionLevel={ext}" if ext >= 0 else ""),
+        "config": {"workload": workload_label(wl_name, n, d, T, ns, ext),
                    "parallelism": (f"trees sharded x{world}, partial sums scattered into NVLink peer memory by the scoring kernel"
                                    if fused else f"trees sharded x{world} + NCCL all-reduce of path sums" if tree_sharded else
                                    f"rows sharded x{world}, forest replicated, no data-path collective"),
