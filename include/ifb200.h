@@ -173,6 +173,18 @@ IFB_API int ifb_peer_signal_device(int32_t device, int32_t world, int32_t rank, 
 IFB_API int ifb_peer_wait_device(int32_t device, int32_t world, const uint32_t *local_flags, uint32_t epoch,
                                  void *stream);
 
+/* Diagnostics of the tensor-core path of fully-extended forests (extensionLevel = d - 1; csrc/score_ext_tc.cu), which
+ * evaluates every hyperplane of the forest (ExtendedUtils.scala:36-55) as one column of a tcgen05 GEMM and uses the
+ * accumulators only as a proven filter in front of the reference's exact comparison.
+ * ifb_ext_tc_info: padded hyperplane width and number of accumulator columns (0: the forest does not qualify and is
+ * scored by the CUDA-core kernels).  ifb_ext_tc_probe: scores the first min(n_rows, 128) rows exactly like
+ * ifb_score_device and additionally returns their raw f32 accumulators acc_device[row][n_columns] (device memory) and
+ * the weight slot of every column col_slot_host[n_columns] (-1: padding), so that a test can measure the accumulation
+ * error of the tensor cores that the bound constant assumes. */
+IFB_API int ifb_ext_tc_info(const ifb_forest *forest, int32_t *k_padded, int32_t *n_columns);
+IFB_API int ifb_ext_tc_probe(const ifb_forest *forest, const float *X, int64_t n_rows, int32_t d, int64_t ld,
+                             int32_t layout, double *scores, float *acc_device, int32_t *col_slot_host, void *stream);
+
 /* prediction column: (score >= threshold) ? 1.0 : 0.0, all 0.0 when threshold <= 0
  * (IF/IsolationForestModel.scala:143-148). */
 IFB_API int ifb_predict_device(int32_t device, const double *scores, int64_t n_rows, double threshold,

@@ -76,6 +76,9 @@ SYMBOLS = {
                                                C.c_void_p, C.c_void_p]),
     "ifb_peer_signal_device": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_uint32, C.c_void_p]),
     "ifb_peer_wait_device": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "ifb_ext_tc_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ifb_ext_tc_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "ifb_predict_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
     "ifb_fit_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                  C.POINTER(FitParams), C.POINTER(C.c_void_p), C.c_void_p]),
@@ -231,6 +234,27 @@ class NativeForest:
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         check(lib().ifb_score_device(self.handle, p(X), n, d, ld, layout, p(scores), p(dsum), p(psum), st))
         return (scores, dsum, psum) if want_parts else scores
+
+    def ext_tc_info(self):
+        """(padded hyperplane width, accumulator columns) of the tensor-core layout; (0, 0) when the forest has none."""
+        kp, nc = C.c_int32(0), C.c_int32(0)
+        check(lib().ifb_ext_tc_info(self.handle, C.byref(kp), C.byref(nc)))
+        return int(kp.value), int(nc.value)
+
+    def ext_tc_probe(self, X):
+        """Diagnostic: scores + raw tensor-core accumulators [rows<=128][columns] + weight slot of every column."""
+        import torch
+
+        n, d, ld, layout = self._layout_of(tuple(X.shape), tuple(X.stride()))
+        _, nc = self.ext_tc_info()
+        rows = min(n, 128)
+        scores = torch.empty(rows, dtype=torch.float64, device=X.device)
+        acc = torch.zeros((rows, nc), dtype=torch.float32, device=X.device)
+        slots = np.empty(nc, np.int32)
+        st = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+        check(lib().ifb_ext_tc_probe(self.handle, C.c_void_p(X.data_ptr()), n, d, ld, layout,
+                                     C.c_void_p(scores.data_ptr()), C.c_void_p(acc.data_ptr()), _np_ptr(slots), st))
+        return scores, acc, slots
 
     def score_partial_device(self, X, path_sum, depth_sum=None, stream=None):
         import torch

@@ -205,6 +205,29 @@ int ifb_peer_wait_device(int32_t device, int32_t world, const uint32_t *local_fl
     return launch_peer_wait(world, local_flags, epoch, (cudaStream_t)stream);
 }
 
+int ifb_ext_tc_info(const ifb_forest *f, int32_t *k_padded, int32_t *n_columns) {
+    IFB_REQUIRE(f && k_padded && n_columns, "null argument");
+    *k_padded = f->tc_ok ? f->tc_kp : 0;
+    *n_columns = f->tc_ok ? f->tc_blocks * 256 : 0;
+    return IFB_OK;
+}
+
+int ifb_ext_tc_probe(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
+                     double *scores, float *acc_device, int32_t *col_slot_host, void *stream) {
+    int rc = check_scoring_args(f, X, n_rows, d, ld, layout);
+    if (rc) return rc;
+    IFB_REQUIRE(f->extended && f->tc_ok, "the forest has no tensor-core layout");
+    IFB_REQUIRE(scores && acc_device && col_slot_host && n_rows >= 1, "null argument");
+    DeviceGuard dg(f->device);
+    const int64_t rows = std::min<int64_t>(n_rows, 128);
+    rc = launch_score_extended_tc(f, X, rows, d, ld, layout, scores, nullptr, nullptr, false, (cudaStream_t)stream, acc_device);
+    IFB_REQUIRE(rc >= 0, "the tensor-core path refused this call (d = %d, forest width %d)", d, f->tc_k);
+    if (rc) return rc;
+    IFB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    IFB_CUDA(cudaMemcpy(col_slot_host, f->d_tc_col_slot, (size_t)f->tc_blocks * 256 * 4, cudaMemcpyDeviceToHost));
+    return IFB_OK;
+}
+
 int ifb_predict_device(int32_t device, const double *scores, int64_t n_rows, double threshold, double *labels,
                        void *stream) {
     IFB_REQUIRE(n_rows == 0 || (scores && labels), "null buffer");

@@ -333,7 +333,14 @@ int build_extended_tables(ifb_forest *f) {
         if ((rc = up((void **)&f->d_ext_blob, blob.data(), blob.size()))) return rc;
         if ((rc = up((void **)&f->d_ext_blob_off, boff.data(), boff.size() * 8))) return rc;
     }
-    return commit();
+    rc = commit();
+    if (rc) return rc;
+    // tensor-core layout (fully-extended forests; a forest that does not qualify simply keeps tc_ok = false)
+    if (f->ext_dense_identity && getenv("IFB_EXT_NO_TC") == nullptr) {
+        rc = build_ext_tc_tables(f, child, hp, leaf, off);
+        if (rc) return rc;
+    }
+    return IFB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -507,6 +514,7 @@ ifb_forest::~ifb_forest() {
     cudaFree(d_gchild);
     cudaFree(d_groot);
     cudaFree(d_ext_arena);   // every d_ext_* table is a slice of it
+    cudaFree(d_tc_arena);    // every d_tc_* table is a slice of it
 }
 
 using namespace ifb;

@@ -155,6 +155,19 @@ struct ifb_forest {
     int64_t ext_blob_max = 0;            // largest blob in bytes
     bool ext_w_safe = false;             // every hyperplane weight is normal with 2^-60 <= |w| <= 2^40
 
+    // ---- tensor-core layout of fully-extended forests (score_ext_tc.cu): every hyperplane of the forest is one
+    // column of a [rows x nodes] GEMM evaluated by tcgen05.mma on fp16 hi/lo splits; 256-column blocks of whole trees
+    bool tc_ok = false;                  // tables below are valid
+    int32_t tc_k = 0, tc_kp = 0;         // hyperplane width and its padding to the K chunk (32)
+    int32_t tc_blocks = 0;               // 256-column blocks
+    void *d_tc_wh = nullptr;             // fp16 [tc_blocks*256][tc_kp]: hi part of the scaled weights
+    void *d_tc_wl = nullptr;             // fp16, lo part
+    unsigned char *d_tc_meta = nullptr;  // [tc_blocks] TcBlockMeta (node records, leaf values, tree roots)
+    int32_t *d_tc_col_slot = nullptr;    // [tc_blocks*256] weight slot of the column's node (-1: padding column)
+    double *d_tc_col_off = nullptr;      // [tc_blocks*256] f64 split offset of the column's node
+    int32_t *d_tc_flag = nullptr;        // set by the column-preparation kernel when a weight row is not fp16-safe
+    unsigned char *d_tc_arena = nullptr;
+
     int64_t device_bytes = 0;
 
     ~ifb_forest();
@@ -194,6 +207,12 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
 int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld,
                           int32_t layout, double *scores, int32_t *depth_sum, float *path_sum,
                           bool accumulate_only, cudaStream_t stream);
+// score_ext_tc.cu: tensor-core path of fully-extended forests; returns -1 when the forest / call does not qualify
+int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const std::vector<int32_t> &hp,
+                        const std::vector<float> &leaf, const std::vector<double> &off);
+int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
+                             double *scores, int32_t *depth_sum, float *path_sum, bool accumulate_only,
+                             cudaStream_t stream, float *probe_out = nullptr);
 // epilogue.cu
 int launch_finalize(const float *path_sum, int64_t n_rows, int32_t total_trees, float avg_path, double *scores,
                     cudaStream_t stream);

@@ -633,6 +633,11 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
     if (n_rows == 0) return IFB_OK;
     IFB_REQUIRE(f->max_feature_index < d, "forest reads feature index %d but the matrix has only %d columns",
                 f->max_feature_index, d);
+    if (getenv("IFB_EXT_GENERIC") == nullptr) {
+        // fully-extended forests: all hyperplanes as one GEMM on the tensor cores (score_ext_tc.cu)
+        const int rc = launch_score_extended_tc(f, X, n_rows, d, ld, layout, scores, depth_sum, path_sum, accumulate_only, stream);
+        if (rc >= 0) return rc;
+    }
     if (f->ext_blob_D > 0 && d <= 64 && getenv("IFB_EXT_GENERIC") == nullptr) {
         ScoreExtDenseParams q;
         q.X = X; q.n_rows = n_rows; q.ld = ld; q.d = d; q.layout = layout;

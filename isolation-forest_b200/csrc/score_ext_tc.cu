@@ -1,0 +1,853 @@
+// Tensor-core scoring of fully-extended isolation forests (every hyperplane dense over all d features) for sm_100a.
+//
+// Replaces ExtendedIsolationTree.pathLength (IF/extended/ExtendedIsolationTree.scala:283-355) and
+// SplitHyperplane.dot (IF/extended/ExtendedUtils.scala:36-55) for the BASELINE shapes with extensionLevel = d-1
+// (config 3: d = 64, config 5: d = 1024).  The per-row dot products of a walk are a contraction
+//     S[row][node] = sum_i x[row][i] * w[node][i]
+// so ALL hyperplanes of the forest are evaluated as one [rows x nodes x d] GEMM on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators in TMEM), and the walk itself only compares accumulators with offsets.
+//
+// Exactness.  The reference decides `sum < offset` with sum = f64 sequential sum of f32-rounded products.  The tensor
+// cores are only a FILTER: operands are split  x' = xh + xl,  w' = wh + wl  into fp16 pairs after an exact power-of-two
+// scaling per row / per node (max |.| in [0.5, 1)), S' = xh.wh + xl.wh + xh.wl is accumulated in f32 by three MMAs per
+// k-step, and a visit is accepted only when
+//     |S' - offset'| > c_k * ||w'||_2 * ||x'||_2            (c_k: bound constant)
+// which proves that the reference's comparison has the same outcome.  Every other visit ("stuck" lane, ~1e-5 of the
+// visits at d = 64, ~1e-3 at d = 1024, and every visit of a row with non-finite / out-of-range features) is decided by
+// the warp cooperatively with the reference's exact arithmetic (f32 product, f64 sum; lane-parallel re-association with
+// its own proven bound, else the sequential order).  Decisions are therefore bit-identical to the reference's.
+//
+// Kernels
+//   ext_tc_prepare_cols   one warp per hyperplane: scale, fp16 hi/lo split, ||w'||, offset' and bound coefficient
+//                         (once per forest).
+//   ext_tc_prepare_rows   per call: row scaling, fp16 hi/lo split, row norm, row-major f32 copy for the exact path.
+//   score_ext_tc_kernel   persistent, warp-specialised: warp 0 = TMA producer (A = rows, B = hyperplanes, 64-byte
+//                         swizzled K-major tiles), warp 1 = tcgen05.mma issuer (128 x 256 x 16 fp16, f32 accumulators,
+//                         two 256-column TMEM buffers), warps 2-5 = epilogue: tcgen05.ld the accumulators, spill them
+//                         to a per-warp shared-memory tile [column][lane], walk the block's trees (4 in flight per
+//                         lane) and add the leaf values in tree order.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "ifb_internal.h"
+
+namespace ifb {
+
+namespace tc {
+
+constexpr int BM = 128;        // rows per tile (TMEM lanes)
+constexpr int BN = 256;        // hyperplanes (accumulator columns) per block
+constexpr int HALF = 128;      // spill unit: trees never straddle a 128-column boundary
+constexpr int BK = 32;         // K chunk in elements (64 bytes of fp16: one 64B swizzle atom row)
+constexpr int STAGES = 3;
+constexpr int MAX_TREES_PER_BLOCK = 64;
+constexpr int MAX_LEAVES_PER_BLOCK = 512;
+constexpr uint32_t A_BYTES = BM * BK * 2;   //  8 KB
+constexpr uint32_t B_BYTES = BN * BK * 2;   // 16 KB
+constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl: 48 KB
+constexpr int EPI_WARPS = 4;
+constexpr int THREADS = (2 + EPI_WARPS) * 32;
+constexpr uint32_t SPILL_BYTES_PER_WARP = HALF * 32 * 4;   // 16 KB
+
+struct Rec {            // one internal node == one accumulator column
+    float thr;          // offset * 2^-s_node, rounded to f32 (scaled domain of the node)
+    float eb;           // bound coefficient: c_k * ||w'||_2 (inflated); the visit is certain iff |dlt| > eb * ||x'||
+    uint32_t refs;      // left | right << 16;  ref = column in the block, or 0x8000 | leaf index
+    int32_t slot;       // weight slot (row of d_ext_w) for the exact path
+};
+struct BlockMeta {
+    Rec rec[BN];
+    float leafv[MAX_LEAVES_PER_BLOCK];
+    uint16_t root[MAX_TREES_PER_BLOCK];
+    int32_t n_trees;
+    int32_t n_trees_half0;    // trees [0, n_trees_half0) have their columns in [0,128), the rest in [128,256)
+    int32_t ncols_half[2];    // used columns of each half
+    int32_t tree0;
+    int32_t pad[3];
+};
+static_assert(sizeof(BlockMeta) % 16 == 0, "bulk copies need 16-byte multiples");
+constexpr uint32_t META_BYTES = sizeof(BlockMeta);
+
+// shared-memory carve-up (offsets from a 1024-aligned base)
+constexpr uint32_t OFF_STAGES = 0;
+constexpr uint32_t OFF_SPILL = OFF_STAGES + STAGES * STAGE_BYTES;
+constexpr uint32_t OFF_META = OFF_SPILL + EPI_WARPS * SPILL_BYTES_PER_WARP;
+constexpr uint32_t OFF_BARS = (OFF_META + 2 * META_BYTES + 15u) & ~15u;
+constexpr int NBARS = 2 * STAGES + 8;
+constexpr uint32_t OFF_TMEMPTR = OFF_BARS + NBARS * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;   // + alignment slack
+
+struct Params {
+    const unsigned char *meta;     // [n_blocks] BlockMeta
+    int32_t n_blocks;
+    int32_t kp;                    // padded K
+    int32_t k;                     // hyperplane width (== d)
+    int64_t n_rows;
+    const float *rnorm;            // [n_rows] ||x'||_2 inflated (+inf: the row never uses the tensor-core decision)
+    const float *rscale;           // [n_rows] 2^-e_row
+    const float *xr;               // [n_rows][kp] row-major f32 copy of the rows (exact path)
+    const float *w;                // d_ext_w [slots][k]
+    const double *wabs;            // d_ext_wabs [slots]
+    const double *col_off;         // [n_blocks*256]
+    int32_t max_depth;
+    int32_t total_trees;
+    float avg_path;
+    int32_t accumulate_only;
+    float eb_scale;                // test hook: multiplies the bound (1 = product behaviour)
+    double *scores;
+    float *path_sum;
+    int32_t *depth_sum;
+    float *probe;                  // diagnostic: raw accumulators of row tile 0, [128][n_blocks*256]
+    unsigned long long *stats;     // [0] stuck visits resolved exactly (diagnostic)
+};
+
+// ---- PTX helpers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a lost transaction / bad descriptor must surface as a launch failure, never as a hung GPU
+// (wall-clock bound of ~4 s on %globaltimer; the longest legitimate wait is one block of MMAs, tens of microseconds).
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (uint32_t spin = 1;; ++spin) {
+        if (mbar_try(bar, parity)) return;
+        if ((spin & 1023u) == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int32_t c0, int32_t c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, f32 accumulate; issued by ONE thread for the whole CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major operand tile with 64-byte swizzle: rows of 64 bytes, 8-row groups 512 bytes apart (SBO), LBO unused,
+// descriptor version 1 (sm_100), layout type 4 = SWIZZLE_64B   (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format = F32 (bits 4-5 = 1), a/b format F16 (0), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- the exact path: one hyperplane decision for one row, evaluated by the whole warp -------------------------------
+// Returns (warp-uniform) whether the reference goes LEFT:  sum_{i ascending} (double) fl32(w_i * x_i)  <  off.
+//   tier 2: the exact addends p_i summed per lane (i = lane, lane+32, ...) and by a shuffle tree -- a re-association,
+//           |S2 - S_ref| <= 2 gamma_{k-1} sum|p_i| <= 4 k 2^-53 max|x| sum|w| =: E2;   |S2 - off| > E2  =>  same outcome;
+//   tier 3: the reference's sequential order (every lane redundantly).
+__device__ __forceinline__ bool exact_left(const float *__restrict__ xr, const float *__restrict__ wr, int k, double off,
+                                           double wabs, int lane) {
+    double acc = 0.0;
+    float mx = 0.f;
+    bool bad = false;
+    for (int i = lane; i < k; i += 32) {
+        const float xv = __ldg(xr + i), wv = __ldg(wr + i);
+        const float a = fabsf(xv);
+        bad = bad || !(a <= 3.0e38f);
+        mx = fmaxf(mx, a);
+        acc = __dadd_rn(acc, (double)__fmul_rn(wv, xv));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    // xor-butterfly: every lane holds the same bits (f64 addition is commutative, the tree is symmetric)
+    const double E2 = 4.0 * (double)k * 0x1.0p-53 * ((double)mx * wabs * 1.0000002);
+    if (!bad && fabs(acc - off) > E2) return acc < off;
+    double sq = 0.0;
+    for (int i = 0; i < k; i++) sq = __dadd_rn(sq, (double)__fmul_rn(__ldg(wr + i), __ldg(xr + i)));
+    return sq < off;
+}
+
+// ---- main kernel ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1)
+score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                    const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, const Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (s32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (base - s32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bars = base + OFF_BARS;
+    auto bar_full = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto bar_empty = [&](int s) { return bars + 8u * (uint32_t)(STAGES + s); };
+    auto bar_tfull = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + b); };
+    auto bar_tempty = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 2 + b); };
+    auto bar_mfull = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 4 + b); };
+    auto bar_mempty = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 6 + b); };
+    uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(sm + OFF_TMEMPTR);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(bar_tfull(b), 1);
+            mbar_init(bar_tempty(b), EPI_WARPS);
+            mbar_init(bar_mfull(b), 1);
+            mbar_init(bar_mempty(b), EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulator buffers); this warp also frees them
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_ptr_s)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    const int64_t n_tiles = (p.n_rows + BM - 1) / BM;
+    const int KC = p.kp / BK;
+    const int NB = p.n_blocks;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int b = 0; b < NB; b++, it++) {
+                    const int mb = (int)(it & 1u);
+                    mbar_wait(bar_mempty(mb), ((it >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(bar_mfull(mb), META_BYTES);
+                    bulk_g2s(base + OFF_META + (uint32_t)mb * META_BYTES, p.meta + (size_t)b * META_BYTES, META_BYTES,
+                             bar_mfull(mb));
+                    for (int kc = 0; kc < KC; kc++) {
+                        mbar_wait(bar_empty(stage), phase ^ 1u);
+                        const uint32_t st = base + OFF_STAGES + (uint32_t)stage * STAGE_BYTES;
+                        mbar_expect_tx(bar_full(stage), STAGE_BYTES);
+                        tma_load_2d(st, &map_xh, kc * BK, (int32_t)(tile * BM), bar_full(stage));
+                        tma_load_2d(st + A_BYTES, &map_xl, kc * BK, (int32_t)(tile * BM), bar_full(stage));
+                        tma_load_2d(st + 2 * A_BYTES, &map_wh, kc * BK, b * BN, bar_full(stage));
+                        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_wl, kc * BK, b * BN, bar_full(stage));
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread issues for the whole CTA =====
+        const uint32_t idesc = umma_idesc_f16(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int b = 0; b < NB; b++, it++) {
+                const int buf = (int)(it & 1u);
+                mbar_wait(bar_tempty(buf), ((it >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
+                for (int kc = 0; kc < KC; kc++) {
+                    mbar_wait(bar_full(stage), phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t st = base + OFF_STAGES + (uint32_t)stage * STAGE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ks++) {
+                            const uint64_t a_h = umma_desc_sw64(st + ks * 32);
+                            const uint64_t a_l = umma_desc_sw64(st + A_BYTES + ks * 32);
+                            const uint64_t b_h = umma_desc_sw64(st + 2 * A_BYTES + ks * 32);
+                            const uint64_t b_l = umma_desc_sw64(st + 2 * A_BYTES + B_BYTES + ks * 32);
+                            umma_f16(d_tmem, a_h, b_h, idesc, (kc | ks) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, a_l, b_h, idesc, 1u);
+                            umma_f16(d_tmem, a_h, b_l, idesc, 1u);
+                        }
+                        umma_commit(bar_empty(stage));   // the stage may be refilled once these MMAs have read it
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (lane == 0) umma_commit(bar_tfull(buf));   // accumulators of this block are complete
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM -> registers -> per-warp spill tile -> tree walks =====
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int ew = warp - 2;                 // spill slot
+        float *spill = reinterpret_cast<float *>(sm + OFF_SPILL + (uint32_t)ew * SPILL_BYTES_PER_WARP);
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t row = tile * BM + q * 32 + lane;
+            const bool live = row < p.n_rows;
+            // dead lanes: r = -1 makes every bound negative, so they are never ambiguous and never touch the exact path
+            const float r = live ? __ldg(p.rnorm + row) * p.eb_scale : -1.f;
+            const float scr = live ? __ldg(p.rscale + row) : 1.f;
+            float s = (p.accumulate_only && live) ? p.path_sum[row] : 0.f;
+            int32_t dsum = (p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
+            for (int b = 0; b < NB; b++, it++) {
+                const int buf = (int)(it & 1u);
+                mbar_wait(bar_mfull(buf), (it >> 1) & 1u);
+                mbar_wait(bar_tfull(buf), (it >> 1) & 1u);
+                tc_fence_after();
+                const BlockMeta *M = reinterpret_cast<const BlockMeta *>(sm + OFF_META + (uint32_t)buf * META_BYTES);
+                const int nt = M->n_trees, nt0 = M->n_trees_half0;
+                for (int h = 0; h < 2; h++) {
+                    const int t0 = h == 0 ? 0 : nt0, t1 = h == 0 ? nt0 : nt;
+                    if (t1 <= t0) continue;   // warp-uniform
+                    const int nc = M->ncols_half[h];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * HALF);
+                    for (int cc = 0; cc * 32 < nc; cc++) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + (uint32_t)cc * 32u, v);
+#pragma unroll
+                        for (int j = 0; j < 32; j++) spill[(cc * 32 + j) * 32 + lane] = __uint_as_float(v[j]);
+                        if (p.probe && tile == 0 && live) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                p.probe[(size_t)row * ((size_t)NB * BN) + (size_t)b * BN + h * HALF + cc * 32 + j] =
+                                    __uint_as_float(v[j]);
+                        }
+                    }
+                    __syncwarp();
+                    // walk the trees of this half, four at a time per lane (independent dependency chains)
+                    for (int tg = t0; tg < t1; tg += 4) {
+                        uint32_t cur[4];
+                        uint32_t stuck = 0;   // bit c: chain c waits for an exact decision
+#pragma unroll
+                        for (int c = 0; c < 4; c++) cur[c] = (live && tg + c < t1) ? (uint32_t)M->root[tg + c] : 0x8000u;
+                        while (true) {
+                            for (int lvl = 0; lvl < p.max_depth; lvl++) {
+                                bool moving = false;
+#pragma unroll
+                                for (int c = 0; c < 4; c++) {
+                                    if (!(cur[c] & 0x8000u) && !((stuck >> c) & 1u)) {
+                                        const int4 rv = *reinterpret_cast<const int4 *>(&M->rec[cur[c]]);
+                                        const float S = spill[(cur[c] & (HALF - 1)) * 32 + lane];
+                                        const float dlt = fmaf(-__int_as_float(rv.x), scr, S);
+                                        const float bnd = __int_as_float(rv.y) * r;
+                                        if (fabsf(dlt) > bnd) {
+                                            cur[c] = dlt < 0.f ? ((uint32_t)rv.z & 0xFFFFu) : ((uint32_t)rv.z >> 16);
+                                            dsum++;
+                                            moving = moving || !(cur[c] & 0x8000u);
+                                        } else {
+                                            stuck |= 1u << c;
+                                        }
+                                    }
+                                }
+                                if (!__any_sync(0xffffffffu, moving)) break;
+                            }
+                            uint32_t sm_mask = __ballot_sync(0xffffffffu, stuck != 0);
+                            if (!sm_mask) break;
+                            // exact decisions, one stuck (lane, chain) at a time, the whole warp cooperating
+                            while (sm_mask) {
+                                const int L = __ffs(sm_mask) - 1;
+                                sm_mask &= sm_mask - 1;
+                                const uint32_t stL = __shfl_sync(0xffffffffu, stuck, L);
+                                const int64_t rowL = __shfl_sync(0xffffffffu, row, L);
+#pragma unroll
+                                for (int c = 0; c < 4; c++) {
+                                    if ((stL >> c) & 1u) {   // warp-uniform
+                                        const uint32_t col = __shfl_sync(0xffffffffu, cur[c], L);
+                                        const Rec rc = M->rec[col];
+                                        const double off = __ldg(p.col_off + (size_t)b * BN + col);
+                                        const bool left = exact_left(p.xr + (size_t)rowL * p.kp, p.w + (size_t)rc.slot * p.k, p.k,
+                                                                     off, __ldg(p.wabs + rc.slot), lane);
+                                        if (lane == L) {
+                                            cur[c] = left ? (rc.refs & 0xFFFFu) : (rc.refs >> 16);
+                                            dsum++;
+                                            stuck &= ~(1u << c);
+                                        }
+                                        if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            if (tg + c < t1) s = s + M->leafv[cur[c] & 0x7FFFu];
+                    }
+                    __syncwarp();   // every lane is done with the spill tile before the next half overwrites it
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar_tempty(buf));
+                    mbar_arrive(bar_mempty(buf));
+                }
+            }
+            if (live) {
+                if (!p.accumulate_only) {
+                    // IF/extended/ExtendedIsolationForestModel.scala:116-119: Float sum / Int, -Float / Float, Math.pow(2, Double)
+                    const float e = __fdiv_rn(s, (float)p.total_trees);
+                    const float z = __fdiv_rn(-e, p.avg_path);
+                    p.scores[row] = exp2((double)z);
+                }
+                if (p.path_sum) p.path_sum[row] = s;
+                if (p.depth_sum) p.depth_sum[row] = dsum;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- per-forest column preparation --------------------------------------------------------------------------------------
+// One warp per accumulator column: power-of-two scaling of the weight row (max |w'| in [0.5, 1)), fp16 hi/lo split,
+// ||w'||_2, the node's offset in its scaled domain and the bound coefficient.
+__global__ void ext_tc_prepare_cols(const float *__restrict__ w, const int32_t *__restrict__ col_slot,
+                                    const double *__restrict__ col_off, int n_cols, int k, int kp, double ck,
+                                    __half *__restrict__ wh, __half *__restrict__ wl, unsigned char *__restrict__ meta,
+                                    int32_t *__restrict__ flag) {
+    const int col = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (col >= n_cols) return;
+    const int slot = col_slot[col];
+    __half *oh = wh + (size_t)col * kp, *ol = wl + (size_t)col * kp;
+    if (slot < 0) {
+        for (int i = lane; i < kp; i += 32) oh[i] = ol[i] = __float2half_rn(0.f);
+        return;
+    }
+    const float *wr = w + (size_t)slot * k;
+    float mx = 0.f;
+    bool bad = false;
+    for (int i = lane; i < k; i += 32) {
+        const float a = fabsf(wr[i]);
+        bad = bad || !(a <= 0x1p60f);
+        mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    bad = __any_sync(0xffffffffu, bad) || (mx > 0.f && mx < 0x1p-60f);
+    int e = 0;
+    if (mx > 0.f) (void)frexpf(mx, &e);        // mx = m * 2^e, m in [0.5, 1)
+    const float sc = ldexpf(1.f, -e);
+    float sq = 0.f;
+    for (int i = lane; i < kp; i += 32) {
+        float hi = 0.f, lo = 0.f;
+        if (i < k && !bad) {
+            const float v = wr[i] * sc;        // exact (power of two; |v| < 1)
+            const __half h = __float2half_rn(v);
+            hi = __half2float(h);
+            lo = v - hi;                       // exact in f32
+            sq = fmaf(v, v, sq);
+        }
+        oh[i] = __float2half_rn(hi);
+        ol[i] = __float2half_rn(lo);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) {
+        Rec *rec = reinterpret_cast<Rec *>(meta + (size_t)(col / BN) * META_BYTES) + (col % BN);
+        const double offs = ldexp(col_off[col], -e);           // exact unless it leaves the f64 range
+        rec->thr = (float)offs;                                // round to nearest; its error is part of c_k
+        // ||w'||_2 from an f32 sum of <= kp squares: relative error <= kp 2^-24, covered by the 2^-10 inflation
+        const double wn = sqrt((double)sq) * (1.0 + 0x1.0p-10);
+        float ebf = (float)(ck * wn);
+        if ((double)ebf < ck * wn) ebf = nextafterf(ebf, INFINITY);
+        rec->eb = ebf;
+        if (bad) atomicExch(flag, 1);
+    }
+}
+
+// ---- per-call row preparation ---------------------------------------------------------------------------------------------
+// 32 rows per CTA staged through shared memory ([row][kp + 1] f32), one warp per 4 rows: power-of-two row scaling
+// (max |x'| in [0.5, 1)), fp16 hi/lo split, ||x'||_2 and a row-major f32 copy for the exact path.
+__global__ void __launch_bounds__(256) ext_tc_prepare_rows(const float *__restrict__ X, int64_t n_rows, int d, int64_t ld,
+                                                           int layout, int kp, __half *__restrict__ xh,
+                                                           __half *__restrict__ xl, float *__restrict__ xr,
+                                                           float *__restrict__ rnorm, float *__restrict__ rscale) {
+    extern __shared__ float tile[];
+    const int pitch = kp + 1;
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (layout == IFB_COL_MAJOR) {
+        // lanes run along rows (coalesced), warps along columns
+        const int64_t row = row0 + lane;
+        for (int c = warp; c < d; c += 8) tile[lane * pitch + c] = row < n_rows ? __ldg(X + (int64_t)c * ld + row) : 0.f;
+    } else {
+        for (int r = warp; r < 32; r += 8) {
+            const int64_t row = row0 + r;
+            for (int c = lane; c < d; c += 32) tile[r * pitch + c] = row < n_rows ? __ldg(X + row * ld + c) : 0.f;
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < 32; r += 8) {
+        const int64_t row = row0 + r;
+        if (row >= n_rows) break;
+        const float *t = tile + r * pitch;
+        float mx = 0.f;
+        bool bad = false;
+        for (int c = lane; c < d; c += 32) {
+            const float a = fabsf(t[c]);
+            bad = bad || !(a <= 0x1p60f);
+            mx = fmaxf(mx, a);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        bad = __any_sync(0xffffffffu, bad) || (mx > 0.f && mx < 0x1p-60f);
+        int e = 0;
+        if (mx > 0.f && !bad) (void)frexpf(mx, &e);
+        const float sc = ldexpf(1.f, -e);
+        float sq = 0.f;
+        __half *oh = xh + (size_t)row * kp, *ol = xl + (size_t)row * kp;
+        float *of = xr + (size_t)row * kp;
+        for (int c = lane; c < kp; c += 32) {
+            const float x = c < d ? t[c] : 0.f;
+            float hi = 0.f, lo = 0.f;
+            if (!bad) {
+                const float v = x * sc;
+                const __half h = __float2half_rn(v);
+                hi = __half2float(h);
+                lo = v - hi;
+                sq = fmaf(v, v, sq);
+            }
+            oh[c] = __float2half_rn(hi);
+            ol[c] = __float2half_rn(lo);
+            of[c] = x;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) {
+            // f32 sum of <= kp squares in [0,1): relative error <= kp 2^-24; inflate by 2^-10
+            rnorm[row] = bad ? __int_as_float(0x7f800000) : sqrtf(sq) * (1.0f + 0x1.0p-10f);
+            rscale[row] = sc;
+        }
+    }
+}
+
+}  // namespace tc
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tc_encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// fp16 matrix [rows][kp] (K contiguous) -> tensor map with a (32 x box_rows) box and the 64-byte swizzle UMMA expects
+int make_tc_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int32_t kp, int box_rows) {
+    EncodeTiledFn enc = tc_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return IFB_ECUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (fp16 %lld x %d, box %d x %d) failed with CUresult %d", (long long)rows, kp, tc::BK,
+                  box_rows, (int)r);
+        return IFB_ECUDA;
+    }
+    return IFB_OK;
+}
+
+// Bound constant of the tensor-core filter (scaled domain):
+//   representation   3 * 2^-22 + 4.004 * sqrt(k) * 2^-25   (two-term fp16 splits of both operands, dropped lo*lo term,
+//                                                            absolute 2^-25 resolution of fp16 below 2^-14)
+//   reference        2^-23                                   ((u + k 2^-53)(1 + u) of the f32 products / f64 sum, and the
+//                                                            f32 rounding of the scaled offset)
+//   accumulation     nsteps * u_acc * 1.01                   (nsteps = 3 kp / 16 MMA accumulation steps, each assumed
+//                                                            accurate to u_acc relative to the sum of magnitudes; u_acc
+//                                                            defaults to 2^-22 = 4 ulp of f32 -- measured on the part, see
+//                                                            profiles/, IFB_TC_UACC_LOG2 overrides)
+double tc_bound_constant(int k, int kp) {
+    static const double u_acc = getenv("IFB_TC_UACC_LOG2") ? std::ldexp(1.0, atoi(getenv("IFB_TC_UACC_LOG2"))) : 0x1.0p-22;
+    const double nsteps = 3.0 * (double)(kp / 16);
+    double ck = 3.0 * 0x1.0p-22 + 4.004 * std::sqrt((double)k) * 0x1.0p-25 + 0x1.0p-23 + nsteps * u_acc * 1.01;
+    return ck * (1.0 + 0x1.0p-12);
+}
+
+}  // namespace
+
+int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const std::vector<int32_t> &hp,
+                        const std::vector<float> &leaf, const std::vector<double> &off) {
+    using namespace tc;
+    const int T = f->num_trees;
+    const int k = f->max_nnz;
+    if (T == 0 || k < 1 || k > 16384 || !f->ext_w_safe) return IFB_OK;
+    const int kp = (k + BK - 1) / BK * BK;
+    // ---- pack whole trees into 128-column halves of 256-column blocks, in tree order ----
+    std::vector<BlockMeta> metas;
+    std::vector<int32_t> col_slot;
+    std::vector<double> col_off;
+    auto new_block = [&](int tree0) {
+        metas.emplace_back();
+        BlockMeta &m = metas.back();
+        std::memset(&m, 0, sizeof m);
+        for (int i = 0; i < BN; i++) {
+            m.rec[i].thr = 0.f;
+            m.rec[i].eb = 0.f;
+            m.rec[i].refs = 0x80008000u;
+            m.rec[i].slot = -1;
+        }
+        m.tree0 = tree0;
+        col_slot.resize(metas.size() * BN, -1);
+        col_off.resize(metas.size() * BN, 0.0);
+    };
+    new_block(0);
+    int half = 0, used = 0, n_leaves = 0;   // state of the block being filled
+    std::vector<int32_t> ref_of;
+    for (int t = 0; t < T; t++) {
+        const int64_t base = f->node_off[t];
+        const int n = f->node_off[t + 1] - f->node_off[t];
+        int m = 0;
+        for (int q = 0; q < n; q++) m += child[base + q] >= 0;
+        if (m > HALF) return IFB_OK;   // a tree wider than the spill unit: the forest keeps the CUDA-core kernels
+        const int nl = n - m;
+        BlockMeta *M = &metas.back();
+        if (used + m > HALF && half == 0) {
+            half = 1;
+            used = 0;
+        }
+        if (used + m > HALF || M->n_trees == MAX_TREES_PER_BLOCK || n_leaves + nl > MAX_LEAVES_PER_BLOCK) {
+            new_block(t);
+            M = &metas.back();
+            half = 0;
+            used = 0;
+            n_leaves = 0;
+        }
+        if (half == 0) M->n_trees_half0++;
+        const int blk = (int)metas.size() - 1;
+        // references of the tree's nodes: internal -> column, leaf -> leaf slot
+        ref_of.assign(n, 0);
+        int ci = 0, li = 0;
+        for (int q = 0; q < n; q++) {
+            if (child[base + q] >= 0) ref_of[q] = half * HALF + used + ci++;
+            else ref_of[q] = 0x8000 | (n_leaves + li++);
+        }
+        for (int q = 0; q < n; q++) {
+            const int64_t g = base + q;
+            if (child[g] >= 0) {
+                const int col = ref_of[q];
+                Rec &r = M->rec[col];
+                r.refs = (uint32_t)ref_of[child[g]] | ((uint32_t)ref_of[child[g] + 1] << 16);
+                r.slot = hp[g];
+                col_slot[(size_t)blk * BN + col] = hp[g];
+                col_off[(size_t)blk * BN + col] = off[g];
+            } else {
+                M->leafv[ref_of[q] & 0x7FFF] = leaf[g];
+            }
+        }
+        M->root[M->n_trees++] = (uint16_t)ref_of[0];
+        used += m;
+        n_leaves += nl;
+        M->ncols_half[half] = used;
+    }
+    const int NB = (int)metas.size();
+    const size_t ncols = (size_t)NB * BN;
+    // ---- one arena: wh | wl | meta | col_slot | col_off | flag ----
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_w = al(ncols * kp * 2), b_meta = al((size_t)NB * META_BYTES), b_slot = al(ncols * 4), b_off = al(ncols * 8);
+    DeviceGuard dg(f->device);
+    IFB_CUDA(cudaMalloc((void **)&f->d_tc_arena, 2 * b_w + b_meta + b_slot + b_off + 256));
+    unsigned char *a = f->d_tc_arena;
+    f->d_tc_wh = a;
+    f->d_tc_wl = a + b_w;
+    f->d_tc_meta = a + 2 * b_w;
+    f->d_tc_col_slot = reinterpret_cast<int32_t *>(a + 2 * b_w + b_meta);
+    f->d_tc_col_off = reinterpret_cast<double *>(a + 2 * b_w + b_meta + b_slot);
+    f->d_tc_flag = reinterpret_cast<int32_t *>(a + 2 * b_w + b_meta + b_slot + b_off);
+    f->device_bytes += (int64_t)(2 * b_w + b_meta + b_slot + b_off + 256);
+    IFB_CUDA(cudaMemcpyAsync(f->d_tc_meta, metas.data(), (size_t)NB * META_BYTES, cudaMemcpyHostToDevice, 0));
+    IFB_CUDA(cudaMemcpyAsync(f->d_tc_col_slot, col_slot.data(), ncols * 4, cudaMemcpyHostToDevice, 0));
+    IFB_CUDA(cudaMemcpyAsync(f->d_tc_col_off, col_off.data(), ncols * 8, cudaMemcpyHostToDevice, 0));
+    IFB_CUDA(cudaMemsetAsync(f->d_tc_flag, 0, 4, 0));
+    const double ck = tc_bound_constant(k, kp);
+    const int warps_per_cta = 8;
+    ext_tc_prepare_cols<<<(unsigned)((ncols + warps_per_cta - 1) / warps_per_cta), warps_per_cta * 32>>>(
+        f->d_ext_w, f->d_tc_col_slot, f->d_tc_col_off, (int)ncols, k, kp, ck, reinterpret_cast<__half *>(f->d_tc_wh),
+        reinterpret_cast<__half *>(f->d_tc_wl), f->d_tc_meta, f->d_tc_flag);
+    IFB_CUDA(cudaGetLastError());
+    count_launch();
+    int32_t flag = 0;
+    IFB_CUDA(cudaMemcpy(&flag, f->d_tc_flag, 4, cudaMemcpyDeviceToHost));   // also waits for the uploads above
+    f->tc_k = k;
+    f->tc_kp = kp;
+    f->tc_blocks = NB;
+    f->tc_ok = flag == 0;
+    return IFB_OK;
+}
+
+int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
+                             double *scores, int32_t *depth_sum, float *path_sum, bool accumulate_only, cudaStream_t stream,
+                             float *probe_out) {
+    using namespace tc;
+    if (!f->tc_ok || d != f->tc_k || getenv("IFB_EXT_NO_TC") != nullptr) return -1;
+    if (n_rows == 0) return IFB_OK;
+    const int kp = f->tc_kp;
+    // test hooks (read per call): IFB_TC_SCALE / IFB_EXT_FAST_SCALE multiply the bound (1e30: every visit takes the exact path)
+    const char *sc_env = getenv("IFB_TC_SCALE") ? getenv("IFB_TC_SCALE") : getenv("IFB_EXT_FAST_SCALE");
+    const float eb_scale = sc_env ? (float)atof(sc_env) : 1.0f;
+    const bool want_stats = getenv("IFB_TC_STATS") != nullptr;
+    // rows are processed in chunks so that the per-call scratch (8 bytes per element) stays below ~8 GB
+    int64_t chunk = ((int64_t)1 << 33) / ((int64_t)kp * 8);
+    chunk = std::max<int64_t>(chunk & ~(int64_t)127, 128 * 1024);
+    chunk = std::min<int64_t>(chunk, (n_rows + 127) & ~(int64_t)127);
+    struct Scratch {
+        cudaStream_t s;
+        void *p = nullptr;
+        ~Scratch() {
+            if (p) cudaFreeAsync(p, s);
+        }
+    } scr{stream};
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_h = al((size_t)chunk * kp * 2), b_f = al((size_t)chunk * kp * 4), b_n = al((size_t)chunk * 4);
+    IFB_CUDA(cudaMallocAsync(&scr.p, 2 * b_h + b_f + 2 * b_n + 256, stream));
+    unsigned char *a = reinterpret_cast<unsigned char *>(scr.p);
+    __half *xh = reinterpret_cast<__half *>(a), *xl = reinterpret_cast<__half *>(a + b_h);
+    float *xr = reinterpret_cast<float *>(a + 2 * b_h);
+    float *rnorm = reinterpret_cast<float *>(a + 2 * b_h + b_f), *rscale = reinterpret_cast<float *>(a + 2 * b_h + b_f + b_n);
+    unsigned long long *stats = reinterpret_cast<unsigned long long *>(a + 2 * b_h + b_f + 2 * b_n);
+    if (want_stats) IFB_CUDA(cudaMemsetAsync(stats, 0, 8, stream));
+
+    CUtensorMap m_wh, m_wl;
+    int rc = make_tc_tmap(&m_wh, f->d_tc_wh, (int64_t)f->tc_blocks * BN, kp, BN);
+    if (rc) return rc;
+    rc = make_tc_tmap(&m_wl, f->d_tc_wl, (int64_t)f->tc_blocks * BN, kp, BN);
+    if (rc) return rc;
+    const int sms = device_sm_count(f->device);
+    IFB_CUDA(cudaFuncSetAttribute(score_ext_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const size_t prep_smem = (size_t)32 * (kp + 1) * 4;
+    IFB_CUDA(cudaFuncSetAttribute(ext_tc_prepare_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+
+    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+        const int64_t rows = std::min<int64_t>(chunk, n_rows - r0);
+        const float *Xc = layout == IFB_COL_MAJOR ? X + r0 : X + r0 * ld;
+        ext_tc_prepare_rows<<<(unsigned)((rows + 31) / 32), 256, prep_smem, stream>>>(Xc, rows, d, ld, layout, kp, xh, xl, xr,
+                                                                                     rnorm, rscale);
+        IFB_CUDA(cudaGetLastError());
+        count_launch();
+        CUtensorMap m_xh, m_xl;
+        rc = make_tc_tmap(&m_xh, xh, rows, kp, BM);
+        if (rc) return rc;
+        rc = make_tc_tmap(&m_xl, xl, rows, kp, BM);
+        if (rc) return rc;
+        Params p;
+        p.meta = f->d_tc_meta;
+        p.n_blocks = f->tc_blocks;
+        p.kp = kp;
+        p.k = f->tc_k;
+        p.n_rows = rows;
+        p.rnorm = rnorm;
+        p.rscale = rscale;
+        p.xr = xr;
+        p.w = f->d_ext_w;
+        p.wabs = f->d_ext_wabs;
+        p.col_off = f->d_tc_col_off;
+        p.max_depth = std::max(f->max_depth, 1);
+        p.total_trees = f->num_trees;
+        p.avg_path = f->avg_path_norm;
+        p.accumulate_only = accumulate_only ? 1 : 0;
+        p.eb_scale = eb_scale;
+        p.scores = scores ? scores + r0 : nullptr;
+        p.path_sum = path_sum ? path_sum + r0 : nullptr;
+        p.depth_sum = depth_sum ? depth_sum + r0 : nullptr;
+        p.probe = (probe_out && r0 == 0) ? probe_out : nullptr;
+        p.stats = want_stats ? stats : nullptr;
+        const int64_t n_tiles = (rows + BM - 1) / BM;
+        const int grid = (int)std::min<int64_t>(n_tiles, sms);
+        score_ext_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(m_xh, m_xl, m_wh, m_wl, p);
+        IFB_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    if (want_stats) {
+        unsigned long long h = 0;
+        IFB_CUDA(cudaMemcpyAsync(&h, stats, 8, cudaMemcpyDeviceToHost, stream));
+        IFB_CUDA(cudaStreamSynchronize(stream));
+        fprintf(stderr, "[ifb] tensor-core path: %llu visits decided exactly (rows %lld, trees %d)\n", h, (long long)n_rows,
+                f->num_trees);
+    }
+    return IFB_OK;
+}
+
+}  // namespace ifb
