@@ -48,7 +48,8 @@ typedef enum ifb_status {
     IFB_ESTATE = 2,  /* bad state           -> IllegalStateException */
     IFB_ECUDA = 3,   /* CUDA runtime error  -> RuntimeException */
     IFB_ENOMEM = 4,  /* host/device OOM     -> RuntimeException */
-    IFB_ENOGPU = 5   /* no usable sm_100 device: the engine has NO CPU fallback */
+    IFB_ENOGPU = 5,  /* no usable sm_100 device: the engine has NO CPU fallback */
+    IFB_ENCCL = 6    /* NCCL missing or failed (ifb_comm_*, ifb_score_sharded)  -> RuntimeException */
 } ifb_status;
 
 typedef enum ifb_layout { IFB_COL_MAJOR = 0, IFB_ROW_MAJOR = 1 } ifb_layout;
@@ -147,6 +148,25 @@ IFB_API int ifb_score_partial_device(const ifb_forest *forest, const float *X, i
 IFB_API int ifb_finalize_scores_device(int32_t device, const float *path_sum, int64_t n_rows,
                                        int32_t total_num_trees, int32_t num_samples, double *scores,
                                        void *stream);
+
+/* The same layout with the collective INSIDE the library, for hosts that have no collective library of their own (a JVM
+ * executor): one communicator per GPU process, bootstrapped from a 128-byte id that one rank creates with
+ * ifb_comm_unique_id and the host framework hands to every rank (Spark: a broadcast variable).  ifb_score_sharded scores
+ * ALL n_rows rows against `forest` (this rank's slice of the ensemble, e.g. built with ifb_fit_device tree_begin/tree_end,
+ * the reference's tree-parallel fit IF/core/SharedTrainLogic.scala:140-149,276-317), sums the per-row path lengths across
+ * ranks with ONE NCCL collective on `stream`, and applies the score epilogue with total_num_trees:
+ *   IFB_SHARD_ALLREDUCE       every rank receives all scores[0 .. n_rows);
+ *   IFB_SHARD_REDUCE_SCATTER  rank r receives only scores[0 .. e-b) of rows [b, e) = [r*per, min(n_rows, (r+1)*per)),
+ *                             per = ceil(n_rows / world); the slice is returned in slice_begin / slice_end.
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls return IFB_ENCCL. */
+typedef struct ifb_comm ifb_comm;
+enum { IFB_SHARD_ALLREDUCE = 0, IFB_SHARD_REDUCE_SCATTER = 1 };
+IFB_API int ifb_comm_unique_id(void *id128 /* 128 bytes out */);
+IFB_API int ifb_comm_init(int32_t device, int32_t world, int32_t rank, const void *id128, ifb_comm **out);
+IFB_API int ifb_comm_destroy(ifb_comm *comm);
+IFB_API int ifb_score_sharded(const ifb_forest *forest, ifb_comm *comm, const float *X, int64_t n_rows, int32_t d,
+                              int64_t ld, int32_t layout, int32_t total_num_trees, int32_t mode, double *scores,
+                              int64_t *slice_begin, int64_t *slice_end, void *stream);
 
 /* Fused variant of the tree-sharded layout (no NCCL on the data path): rows are cut into `world` contiguous
  * ownership ranges row_cuts[0..world]; rank r's scoring kernel writes its partial path-length sum of every row

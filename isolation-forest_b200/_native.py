@@ -17,7 +17,9 @@ IFB_OK = 0
 COL_MAJOR = 0
 ROW_MAJOR = 1
 
-_STATUS_EXC = {1: ValueError, 2: RuntimeError, 3: RuntimeError, 4: MemoryError, 5: RuntimeError}
+_STATUS_EXC = {1: ValueError, 2: RuntimeError, 3: RuntimeError, 4: MemoryError, 5: RuntimeError, 6: RuntimeError}
+SHARD_ALLREDUCE = 0
+SHARD_REDUCE_SCATTER = 1
 
 
 class NativeError(RuntimeError):
@@ -67,6 +69,12 @@ SYMBOLS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "ifb_finalize_scores_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                              C.c_void_p]),
+    "ifb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "ifb_comm_init": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ifb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "ifb_score_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                    C.c_void_p]),
     "ifb_ipc_export": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p]),
     "ifb_ipc_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ifb_ipc_close": (C.c_int, [C.c_int32, C.c_void_p]),
@@ -263,6 +271,42 @@ class NativeForest:
         st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(X.device).cuda_stream)
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         check(lib().ifb_score_partial_device(self.handle, p(X), n, d, ld, layout, p(path_sum), p(depth_sum), st))
+
+
+class NativeComm:
+    """NCCL communicator owned by libifb200.so (ifb_comm_init): one per GPU process."""
+
+    def __init__(self, device: int, world: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        out = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        check(lib().ifb_comm_init(device, world, rank, buf, C.byref(out)))
+        self._h, self.world, self.rank = out, world, rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().ifb_comm_unique_id(buf))
+        return bytes(buf.raw)
+
+    def score_sharded(self, forest: "NativeForest", X, total_num_trees: int, mode: int = SHARD_ALLREDUCE, stream=None):
+        """Returns (scores, begin, end): all rows (all-reduce) or this rank's slice (reduce-scatter)."""
+        import torch
+
+        n, d, ld, layout = NativeForest._layout_of(tuple(X.shape), tuple(X.stride()))
+        per = (n + self.world - 1) // self.world
+        rows = n if mode == SHARD_ALLREDUCE else max(0, min(n, (self.rank + 1) * per) - min(n, self.rank * per))
+        scores = torch.empty(rows, dtype=torch.float64, device=X.device)
+        b, e = C.c_int64(0), C.c_int64(0)
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(X.device).cuda_stream)
+        check(lib().ifb_score_sharded(forest.handle, self._h, C.c_void_p(X.data_ptr()), n, d, ld, layout, total_num_trees,
+                                      mode, C.c_void_p(scores.data_ptr()), C.byref(b), C.byref(e), st))
+        return scores, int(b.value), int(e.value)
+
+    def close(self):
+        if self._h is not None:
+            lib().ifb_comm_destroy(self._h)
+            self._h = None
 
 
 def finalize_scores_device(path_sum, total_num_trees: int, num_samples: int, scores=None, stream=None):

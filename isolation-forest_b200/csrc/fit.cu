@@ -422,6 +422,12 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
         if (tid == 0) {
             if (sp == 0) {
                 sh.done = 1;
+            } else if (nnodes >= p.cap) {
+                // Degenerate splits (a column holding both -inf and +inf, or split == min) send every row right and
+                // leave a 0-row left leaf level after level; never write past this tree's slice of the tables: stop
+                // and report one node too many, which the host turns into an error.
+                sh.done = 1;
+                nnodes = p.cap + 1;
             } else {
                 sh.done = 0;
                 sh.cur = sh.stack[--sp];
@@ -737,7 +743,9 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     const int k = ext ? std::min(prm->extension_level + 1, prm->num_features) : 1;
     // node capacity: standard trees have <= 2n-1 nodes; extended trees may keep empty leaves, bound by the
     // complete tree of height hl, but never more than 2*internal+1 with internal <= min(2^hl - 1, ...)
-    int64_t cap = ext ? std::min<int64_t>((1LL << (hl + 1)) - 1, 4LL * n + 1) : 2LL * n - 1;
+    // (a standard tree with degenerate splits can carry up to two extra nodes per level: 0-row leaves, which
+    // ifb_forest_create_standard then rejects with the reference's ExternalNode requirement, IF/Nodes.scala:27-31)
+    int64_t cap = ext ? std::min<int64_t>((1LL << (hl + 1)) - 1, 4LL * n + 1) : 2LL * n - 1 + 2LL * hl + 2;
     int64_t cap_internal = ext ? std::min<int64_t>((1LL << hl) - 1, 2LL * n) : 0;
     if (ext) cap = std::min<int64_t>(cap, 2 * cap_internal + 1);
     int hcap = 1;
@@ -954,16 +962,21 @@ extern "C" int ifb_fit_host(int32_t device, const float *X, int64_t n_rows, int3
     IFB_REQUIRE(layout == IFB_COL_MAJOR ? ld >= n_rows : ld >= d, "leading dimension %lld too small", (long long)ld);
     DeviceGuard dg(device);
     // The builder touches only numEstimators * numSamples rows, but which ones is decided on the device, so
-    // the matrix is staged whole (it is needed on the device for the threshold pass of fit anyway).
-    const size_t elems = (size_t)(layout == IFB_COL_MAJOR ? (int64_t)d * ld : n_rows * ld);
+    // the matrix is staged whole (it is needed on the device for the threshold pass of fit anyway).  Only the
+    // addressed extent of the caller's (possibly strided) buffer is read: (d-1)*ld + n_rows resp. (n_rows-1)*ld + d
+    // elements; the device copy is compact.
+    const bool cm = layout == IFB_COL_MAJOR;
+    const int64_t ld_dev = cm ? ((n_rows + 3) & ~3LL) : d;
+    const size_t width = (size_t)(cm ? n_rows : d) * 4, height = (size_t)(cm ? d : n_rows);
     float *dX = nullptr;
-    IFB_CUDA(cudaMalloc((void **)&dX, elems * 4));
-    cudaError_t e = cudaMemcpy(dX, X, elems * 4, cudaMemcpyHostToDevice);
+    IFB_CUDA(cudaMalloc((void **)&dX, (size_t)ld_dev * height * 4));
+    cudaError_t e = cudaMemcpy2D(dX, (size_t)ld_dev * 4, X, (size_t)ld * 4, width, height, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cudaFree(dX);
         set_error("host->device copy failed: %s", cudaGetErrorString(e));
         return IFB_ECUDA;
     }
+    ld = ld_dev;
     int rc = ifb_fit_device(device, dX, n_rows, d, ld, layout, prm, out, nullptr);
     cudaFree(dX);
     return rc;

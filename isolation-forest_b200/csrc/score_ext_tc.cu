@@ -9,9 +9,9 @@
 //
 // Exactness.  The reference decides `sum < offset` with sum = f64 sequential sum of f32-rounded products.  The tensor
 // cores are only a FILTER: operands are split  x' = xh + xl,  w' = wh + wl  into fp16 pairs after an exact power-of-two
-// scaling per row / per node (max |.| in [0.5, 1)), S' = xh.wh + xl.wh + xh.wl is accumulated in f32 by three MMAs per
-// k-step, and a visit is accepted only when
-//     |S' - offset'| > c_k * ||w'||_2 * ||x'||_2            (c_k: bound constant)
+// scaling per row (||x'||_2 in [0.5, 1)) / per node (max |w'| in [0.5, 1)), S' = xh.wh + xl.wh + xh.wl is accumulated
+// in f32 by three MMAs per k-step, and a visit is accepted only when
+//     |S' - offset'| > c_k * ||w'||_2 * 1  >=  c_k * ||w'||_2 * ||x'||_2      (c_k: bound constant)
 // which proves that the reference's comparison has the same outcome.  Every other visit ("stuck" lane, ~1e-5 of the
 // visits at d = 64, ~1e-3 at d = 1024, and every visit of a row with non-finite / out-of-range features) is decided by
 // the warp cooperatively with the reference's exact arithmetic (f32 product, f64 sum; lane-parallel re-association with
@@ -23,9 +23,13 @@
 //   ext_tc_prepare_rows   per call: row scaling, fp16 hi/lo split, row norm, row-major f32 copy for the exact path.
 //   score_ext_tc_kernel   persistent, warp-specialised: warp 0 = TMA producer (A = rows, B = hyperplanes, 64-byte
 //                         swizzled K-major tiles), warp 1 = tcgen05.mma issuer (128 x 256 x 16 fp16, f32 accumulators,
-//                         two 256-column TMEM buffers), warps 2-5 = epilogue: tcgen05.ld the accumulators, spill them
-//                         to a per-warp shared-memory tile [column][lane], walk the block's trees (4 in flight per
-//                         lane) and add the leaf values in tree order.
+//                         two 256-column TMEM buffers), warps 2-9 = epilogue.  A pair of epilogue warps shares a TMEM lane
+//                         quarter (32 rows); one drains and walks the trees of columns [0,128) of every block, the
+//                         other those of [128,256): tcgen05.ld 32 accumulators at a time, turn every one into two
+//                         bits (left? / ambiguous?) appended to per-lane mask words (no per-column store), park the
+//                         8 mask words in shared memory, walk the half's trees on the masks (4 chains in flight per
+//                         lane), resolve ambiguous visits exactly, and hand the leaf values to the pair's first warp,
+//                         which adds them in tree order (the reference's sequential f32 sum).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -33,6 +37,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "ifb_internal.h"
 
@@ -42,43 +47,44 @@ namespace tc {
 
 constexpr int BM = 128;        // rows per tile (TMEM lanes)
 constexpr int BN = 256;        // hyperplanes (accumulator columns) per block
-constexpr int HALF = 128;      // spill unit: trees never straddle a 128-column boundary
+constexpr int MAX_TREE_COLS = 160;   // widest tree (internal nodes) the layout accepts
+constexpr int MAX_GROUP_SPAN = 192;  // columns one epilogue warp drains per block, from a 32-aligned base (6 LDTM chunks)
 constexpr int BK = 32;         // K chunk in elements (64 bytes of fp16: one 64B swizzle atom row)
 constexpr int STAGES = 3;
-constexpr int MAX_TREES_PER_BLOCK = 64;
+constexpr int MAX_TREES_PER_BLOCK = 16;
 constexpr int MAX_LEAVES_PER_BLOCK = 512;
 constexpr uint32_t A_BYTES = BM * BK * 2;   //  8 KB
 constexpr uint32_t B_BYTES = BN * BK * 2;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl: 48 KB
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int META_RING = 4;     // block descriptors in flight: the producer runs ahead of the epilogue by up to 4 blocks
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
-constexpr uint32_t SPILL_BYTES_PER_WARP = HALF * 32 * 4;   // 16 KB
 
-struct Rec {            // one internal node == one accumulator column
-    float thr;          // offset * 2^-s_node, rounded to f32 (scaled domain of the node)
-    float eb;           // bound coefficient: c_k * ||w'||_2 (inflated); the visit is certain iff |dlt| > eb * ||x'||
-    uint32_t refs;      // left | right << 16;  ref = column in the block, or 0x8000 | leaf index
-    int32_t slot;       // weight slot (row of d_ext_w) for the exact path
-};
 struct BlockMeta {
-    Rec rec[BN];
+    float2 ne[BN];            // per column (= internal node): {-offset', bound}: offset' = offset * 2^-s_node rounded to
+                              // f32; the visit is certain iff |S' - offset' * 2^-e_row| >= bound  (bound > c_k ||w'||)
+    uint32_t refs[BN];        // left | right << 16;  ref = column in the block, or 0x8000 | leaf index
+    int32_t slot[BN];         // weight slot (row of d_ext_w) for the exact path; -1: padding column
     float leafv[MAX_LEAVES_PER_BLOCK];
     uint16_t root[MAX_TREES_PER_BLOCK];
-    int32_t n_trees;
-    int32_t n_trees_half0;    // trees [0, n_trees_half0) have their columns in [0,128), the rest in [128,256)
-    int32_t ncols_half[2];    // used columns of each half
+    int32_t n_trees;          // consecutive trees of the ensemble, columns assigned in tree order
+    int32_t n_trees_g0;       // trees [0, n_trees_g0) are drained and walked by the first warp of a pair, the rest by the second
+    int32_t gbase[2];         // first column of each group, rounded down to a multiple of 32
+    int32_t gchunks[2];       // 32-column chunks each group drains (<= 6)
     int32_t tree0;
-    int32_t pad[3];
+    int32_t pad;
 };
 static_assert(sizeof(BlockMeta) % 16 == 0, "bulk copies need 16-byte multiples");
 constexpr uint32_t META_BYTES = sizeof(BlockMeta);
 
 // shared-memory carve-up (offsets from a 1024-aligned base)
 constexpr uint32_t OFF_STAGES = 0;
-constexpr uint32_t OFF_SPILL = OFF_STAGES + STAGES * STAGE_BYTES;
-constexpr uint32_t OFF_META = OFF_SPILL + EPI_WARPS * SPILL_BYTES_PER_WARP;
-constexpr uint32_t OFF_BARS = (OFF_META + 2 * META_BYTES + 15u) & ~15u;
-constexpr int NBARS = 2 * STAGES + 8;
+constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;          // per epilogue warp: lm[8][32], am[8][32]
+constexpr uint32_t OFF_LV = OFF_MASKS + EPI_WARPS * 2048;                  // [2][MAX_TREES_PER_BLOCK][128] leaf values
+constexpr uint32_t OFF_DSX = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;    // [128] depth counts of the second warps
+constexpr uint32_t OFF_META = OFF_DSX + BM * 4;
+constexpr uint32_t OFF_BARS = (OFF_META + META_RING * META_BYTES + 15u) & ~15u;
+constexpr int NBARS = 2 * STAGES + 4 + 2 * META_RING;
 constexpr uint32_t OFF_TMEMPTR = OFF_BARS + NBARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;   // + alignment slack
 
@@ -88,8 +94,9 @@ struct Params {
     int32_t kp;                    // padded K
     int32_t k;                     // hyperplane width (== d)
     int64_t n_rows;
-    const float *rnorm;            // [n_rows] ||x'||_2 inflated (+inf: the row never uses the tensor-core decision)
     const float *rscale;           // [n_rows] 2^-e_row
+    const uint8_t *rflag;          // [n_rows] 0: ordinary row, 1: all-zero row (never ambiguous), 2: non-finite / out-of-range
+                                   //          features (every visit takes the exact path)
     const float *xr;               // [n_rows][kp] row-major f32 copy of the rows (exact path)
     const float *w;                // d_ext_w [slots][k]
     const double *wabs;            // d_ext_wabs [slots]
@@ -137,6 +144,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (uint32_t spin = 1;; ++spin) {
+        if (mbar_try(bar, parity)) return;
+        if ((spin & 1023u) == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+// Same, for the single-lane producer / MMA roles: they have slack, so they back off between polls instead of taking
+// issue slots from the epilogue warps that share their scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (uint32_t spin = 1;; ++spin) {
+        __nanosleep(64);
         if (mbar_try(bar, parity)) return;
         if ((spin & 1023u) == 0) {
             unsigned long long t1;
@@ -229,6 +252,7 @@ __device__ __forceinline__ bool exact_left(const float *__restrict__ xr, const f
 }
 
 // ---- main kernel ------------------------------------------------------------------------------------------------------
+template <bool HOOK>
 __global__ void __launch_bounds__(THREADS, 1)
 score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                     const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, const Params p) {
@@ -242,7 +266,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     auto bar_tfull = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + b); };
     auto bar_tempty = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 2 + b); };
     auto bar_mfull = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 4 + b); };
-    auto bar_mempty = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 6 + b); };
+    auto bar_mempty = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 4 + META_RING + b); };
     uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(sm + OFF_TMEMPTR);
 
     if (threadIdx.x == 0) {
@@ -253,6 +277,8 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         for (int b = 0; b < 2; b++) {
             mbar_init(bar_tfull(b), 1);
             mbar_init(bar_tempty(b), EPI_WARPS);
+        }
+        for (int b = 0; b < META_RING; b++) {
             mbar_init(bar_mfull(b), 1);
             mbar_init(bar_mempty(b), EPI_WARPS);
         }
@@ -280,13 +306,13 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int b = 0; b < NB; b++, it++) {
-                    const int mb = (int)(it & 1u);
-                    mbar_wait(bar_mempty(mb), ((it >> 1) & 1u) ^ 1u);
+                    const int mb = (int)(it % META_RING);
+                    mbar_wait_relaxed(bar_mempty(mb), ((it / META_RING) & 1u) ^ 1u);
                     mbar_expect_tx(bar_mfull(mb), META_BYTES);
                     bulk_g2s(base + OFF_META + (uint32_t)mb * META_BYTES, p.meta + (size_t)b * META_BYTES, META_BYTES,
                              bar_mfull(mb));
                     for (int kc = 0; kc < KC; kc++) {
-                        mbar_wait(bar_empty(stage), phase ^ 1u);
+                        mbar_wait_relaxed(bar_empty(stage), phase ^ 1u);
                         const uint32_t st = base + OFF_STAGES + (uint32_t)stage * STAGE_BYTES;
                         mbar_expect_tx(bar_full(stage), STAGE_BYTES);
                         tma_load_2d(st, &map_xh, kc * BK, (int32_t)(tile * BM), bar_full(stage));
@@ -303,20 +329,20 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread issues for the whole CTA =====
-        const uint32_t idesc = umma_idesc_f16(BM, BN);
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int b = 0; b < NB; b++, it++) {
-                const int buf = (int)(it & 1u);
-                mbar_wait(bar_tempty(buf), ((it >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
-                for (int kc = 0; kc < KC; kc++) {
-                    mbar_wait(bar_full(stage), phase);
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int b = 0; b < NB; b++, it++) {
+                    const int buf = (int)(it & 1u);
+                    mbar_wait(bar_tempty(buf), ((it >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
                     tc_fence_after();
-                    if (lane == 0) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
+                    for (int kc = 0; kc < KC; kc++) {
+                        mbar_wait(bar_full(stage), phase);
+                        tc_fence_after();
                         const uint32_t st = base + OFF_STAGES + (uint32_t)stage * STAGE_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ks++) {
@@ -329,123 +355,166 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                             umma_f16(d_tmem, a_h, b_l, idesc, 1u);
                         }
                         umma_commit(bar_empty(stage));   // the stage may be refilled once these MMAs have read it
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
                     }
-                    __syncwarp();
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    umma_commit(bar_tfull(buf));   // accumulators of this block are complete
                 }
-                if (lane == 0) umma_commit(bar_tfull(buf));   // accumulators of this block are complete
-                __syncwarp();
             }
         }
     } else {
-        // ===== epilogue warps: TMEM -> registers -> per-warp spill tile -> tree walks =====
-        const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int ew = warp - 2;                 // spill slot
-        float *spill = reinterpret_cast<float *>(sm + OFF_SPILL + (uint32_t)ew * SPILL_BYTES_PER_WARP);
+        // ===== epilogue warps: TMEM -> registers -> decision masks -> tree walks =====
+        const int ew = warp - 2;                 // 0..7
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access (rows q*32 .. q*32+31 of the tile)
+        const int hh = ew >> 2;                  // the tree group of every block this warp drains and walks
+        uint32_t *lm = reinterpret_cast<uint32_t *>(sm + OFF_MASKS + (uint32_t)ew * 2048u);   // [8][32] "left" bits
+        uint32_t *am = lm + 256;                                                             // [8][32] "ambiguous" bits
+        float *lvbuf = reinterpret_cast<float *>(sm + OFF_LV);
+        int32_t *dsx = reinterpret_cast<int32_t *>(sm + OFF_DSX);
+        const int pair_bar = 1 + q;              // named barrier of the two warps that share this lane quarter
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t row = tile * BM + q * 32 + lane;
             const bool live = row < p.n_rows;
-            // dead lanes: r = -1 makes every bound negative, so they are never ambiguous and never touch the exact path
-            const float r = live ? __ldg(p.rnorm + row) * p.eb_scale : -1.f;
             const float scr = live ? __ldg(p.rscale + row) : 1.f;
-            float s = (p.accumulate_only && live) ? p.path_sum[row] : 0.f;
-            int32_t dsum = (p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
+            const uint32_t flag = live ? (uint32_t)__ldg(p.rflag + row) : 1u;   // dead lanes behave like zero rows
+            const uint32_t amb_or = flag == 2u ? 0xFFFFFFFFu : 0u;               // out-of-range row: everything ambiguous
+            const uint32_t amb_and = flag == 1u ? 0u : 0xFFFFFFFFu;              // zero row: S' = 0 exactly, never ambiguous
+            float s = (hh == 0 && p.accumulate_only && live) ? p.path_sum[row] : 0.f;
+            int32_t dsum = (hh == 0 && p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
             for (int b = 0; b < NB; b++, it++) {
                 const int buf = (int)(it & 1u);
-                mbar_wait(bar_mfull(buf), (it >> 1) & 1u);
+                const int mb = (int)(it % META_RING);
+                mbar_wait(bar_mfull(mb), (it / META_RING) & 1u);
                 mbar_wait(bar_tfull(buf), (it >> 1) & 1u);
                 tc_fence_after();
-                const BlockMeta *M = reinterpret_cast<const BlockMeta *>(sm + OFF_META + (uint32_t)buf * META_BYTES);
-                const int nt = M->n_trees, nt0 = M->n_trees_half0;
-                for (int h = 0; h < 2; h++) {
-                    const int t0 = h == 0 ? 0 : nt0, t1 = h == 0 ? nt0 : nt;
-                    if (t1 <= t0) continue;   // warp-uniform
-                    const int nc = M->ncols_half[h];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * HALF);
-                    for (int cc = 0; cc * 32 < nc; cc++) {
+                const BlockMeta *M = reinterpret_cast<const BlockMeta *>(sm + OFF_META + (uint32_t)mb * META_BYTES);
+                const int nt = M->n_trees, nt0 = M->n_trees_g0;
+                const int t0 = hh == 0 ? 0 : nt0, t1 = hh == 0 ? nt0 : nt;
+                const int gbase = M->gbase[hh], nchunks = M->gchunks[hh];
+                // ---- drain: 32 accumulators at a time -> two bits each, appended to the mask words ----
+                if (t1 > t0) {   // warp-uniform
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + gbase);
+                    for (int cc = 0; cc < nchunks; cc++) {
                         uint32_t v[32];
                         tmem_ld32(taddr + (uint32_t)cc * 32u, v);
+                        const float2 *ne = M->ne + gbase + cc * 32;
+                        uint32_t Lq[4] = {0, 0, 0, 0}, Aq[4] = {0, 0, 0, 0};   // four short dependency chains per mask
 #pragma unroll
-                        for (int j = 0; j < 32; j++) spill[(cc * 32 + j) * 32 + lane] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; j++) {
+                            const float2 c = ne[j];                                   // warp-uniform (broadcast) load
+                            const float dlt = fmaf(c.x, scr, __uint_as_float(v[j]));  // S' - offset' * 2^-e_row
+                            const float bound = HOOK ? c.y * p.eb_scale : c.y;
+                            const float tt = fabsf(dlt) - bound;                      // < 0: the visit is ambiguous
+                            Lq[j >> 3] = __funnelshift_l(__float_as_uint(dlt), Lq[j >> 3], 1);   // append the sign bits
+                            Aq[j >> 3] = __funnelshift_l(__float_as_uint(tt), Aq[j >> 3], 1);
+                        }
+                        // column j of the chunk ends up in bit 31 - j
+                        const uint32_t L = (Lq[0] << 24) | (Lq[1] << 16) | (Lq[2] << 8) | Lq[3];
+                        const uint32_t A = (Aq[0] << 24) | (Aq[1] << 16) | (Aq[2] << 8) | Aq[3];
+                        lm[cc * 32 + lane] = L;
+                        am[cc * 32 + lane] = (A | amb_or) & amb_and;
                         if (p.probe && tile == 0 && live) {
 #pragma unroll
                             for (int j = 0; j < 32; j++)
-                                p.probe[(size_t)row * ((size_t)NB * BN) + (size_t)b * BN + h * HALF + cc * 32 + j] =
+                                p.probe[(size_t)row * ((size_t)NB * BN) + (size_t)b * BN + gbase + cc * 32 + j] =
                                     __uint_as_float(v[j]);
                         }
                     }
-                    __syncwarp();
-                    // walk the trees of this half, four at a time per lane (independent dependency chains)
-                    for (int tg = t0; tg < t1; tg += 4) {
-                        uint32_t cur[4];
-                        uint32_t stuck = 0;   // bit c: chain c waits for an exact decision
+                }
+                // the accumulator buffer is free as soon as both halves are in registers / masks
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty(buf));
+                // ---- walk this half's trees on the masks, four chains in flight per lane ----
+                float *lv = lvbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + q * 32 + lane;
+                auto walk_group = [&](auto nch_tag, int tg) {
+                    constexpr int NCH = decltype(nch_tag)::value;
+                    uint32_t cur[NCH];
+                    uint32_t stuck = 0;   // bit c: chain c waits for an exact decision
 #pragma unroll
-                        for (int c = 0; c < 4; c++) cur[c] = (live && tg + c < t1) ? (uint32_t)M->root[tg + c] : 0x8000u;
-                        while (true) {
-                            for (int lvl = 0; lvl < p.max_depth; lvl++) {
-                                bool moving = false;
+                    for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[tg + c] : 0x8000u;
+                    while (true) {
+                        // branch-free levels: a chain that sits on a leaf or waits for an exact decision stays put, so
+                        // the NCH chains' loads issue back to back (no divergence, no per-level vote)
+#pragma unroll 1
+                        for (int lvl = 0; lvl < p.max_depth; lvl++) {
 #pragma unroll
-                                for (int c = 0; c < 4; c++) {
-                                    if (!(cur[c] & 0x8000u) && !((stuck >> c) & 1u)) {
-                                        const int4 rv = *reinterpret_cast<const int4 *>(&M->rec[cur[c]]);
-                                        const float S = spill[(cur[c] & (HALF - 1)) * 32 + lane];
-                                        const float dlt = fmaf(-__int_as_float(rv.x), scr, S);
-                                        const float bnd = __int_as_float(rv.y) * r;
-                                        if (fabsf(dlt) > bnd) {
-                                            cur[c] = dlt < 0.f ? ((uint32_t)rv.z & 0xFFFFu) : ((uint32_t)rv.z >> 16);
-                                            dsum++;
-                                            moving = moving || !(cur[c] & 0x8000u);
-                                        } else {
-                                            stuck |= 1u << c;
-                                        }
-                                    }
-                                }
-                                if (!__any_sync(0xffffffffu, moving)) break;
+                            for (int c = 0; c < NCH; c++) {
+                                const uint32_t cu = cur[c];
+                                const uint32_t cl = (cu - (uint32_t)gbase) & (BN - 1);   // column relative to the group's base
+                                const uint32_t idx = (cl & 224u) | (uint32_t)lane, sh = (~cl) & 31u;
+                                const uint32_t Lw = lm[idx], Aw = am[idx];
+                                const uint32_t rf = M->refs[cu & (BN - 1)];
+                                const uint32_t amb = (Aw >> sh) & 1u, lft = (Lw >> sh) & 1u;
+                                const uint32_t act = ((cu >> 15) ^ 1u) & ((stuck >> c) ^ 1u) & 1u;
+                                const uint32_t adv = act & (amb ^ 1u);
+                                cur[c] = adv ? (lft ? (rf & 0xFFFFu) : (rf >> 16)) : cu;
+                                dsum += (int32_t)adv;
+                                stuck |= (act & amb) << c;
                             }
-                            uint32_t sm_mask = __ballot_sync(0xffffffffu, stuck != 0);
-                            if (!sm_mask) break;
-                            // exact decisions, one stuck (lane, chain) at a time, the whole warp cooperating
-                            while (sm_mask) {
-                                const int L = __ffs(sm_mask) - 1;
-                                sm_mask &= sm_mask - 1;
-                                const uint32_t stL = __shfl_sync(0xffffffffu, stuck, L);
-                                const int64_t rowL = __shfl_sync(0xffffffffu, row, L);
+                        }
+                        uint32_t sm_mask = __ballot_sync(0xffffffffu, stuck != 0);
+                        if (!sm_mask) break;
+                        // exact decisions, one stuck (lane, chain) at a time, the whole warp cooperating
+                        while (sm_mask) {
+                            const int Ls = __ffs(sm_mask) - 1;
+                            sm_mask &= sm_mask - 1;
+                            const uint32_t stL = __shfl_sync(0xffffffffu, stuck, Ls);
+                            const int64_t rowL = __shfl_sync(0xffffffffu, row, Ls);
 #pragma unroll
-                                for (int c = 0; c < 4; c++) {
-                                    if ((stL >> c) & 1u) {   // warp-uniform
-                                        const uint32_t col = __shfl_sync(0xffffffffu, cur[c], L);
-                                        const Rec rc = M->rec[col];
-                                        const double off = __ldg(p.col_off + (size_t)b * BN + col);
-                                        const bool left = exact_left(p.xr + (size_t)rowL * p.kp, p.w + (size_t)rc.slot * p.k, p.k,
-                                                                     off, __ldg(p.wabs + rc.slot), lane);
-                                        if (lane == L) {
-                                            cur[c] = left ? (rc.refs & 0xFFFFu) : (rc.refs >> 16);
-                                            dsum++;
-                                            stuck &= ~(1u << c);
-                                        }
-                                        if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
+                            for (int c = 0; c < NCH; c++) {
+                                if ((stL >> c) & 1u) {   // warp-uniform
+                                    const uint32_t col = __shfl_sync(0xffffffffu, cur[c], Ls);
+                                    const uint32_t rf = M->refs[col];
+                                    const int32_t slot = M->slot[col];
+                                    const double off = __ldg(p.col_off + (size_t)b * BN + col);
+                                    const bool left = exact_left(p.xr + (size_t)rowL * p.kp, p.w + (size_t)slot * p.k, p.k, off,
+                                                                 __ldg(p.wabs + slot), lane);
+                                    if (lane == Ls) {
+                                        cur[c] = left ? (rf & 0xFFFFu) : (rf >> 16);
+                                        dsum++;
+                                        stuck &= ~(1u << c);
                                     }
+                                    if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                                 }
                             }
                         }
-#pragma unroll
-                        for (int c = 0; c < 4; c++)
-                            if (tg + c < t1) s = s + M->leafv[cur[c] & 0x7FFFu];
                     }
-                    __syncwarp();   // every lane is done with the spill tile before the next half overwrites it
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) lv[(tg + c) * BM] = M->leafv[cur[c] & 0x7FFFu];
+                };
+                for (int tg = t0; tg < t1;) {
+                    const int left_trees = t1 - tg;
+                    if (left_trees >= 4) {
+                        walk_group(std::integral_constant<int, 4>{}, tg);
+                        tg += 4;
+                    } else if (left_trees == 3) {
+                        walk_group(std::integral_constant<int, 3>{}, tg);
+                        tg += 3;
+                    } else if (left_trees == 2) {
+                        walk_group(std::integral_constant<int, 2>{}, tg);
+                        tg += 2;
+                    } else {
+                        walk_group(std::integral_constant<int, 1>{}, tg);
+                        tg += 1;
+                    }
                 }
-                tc_fence_before();
+                // ---- the pair meets; its first warp adds the block's leaf values in tree order ----
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                if (hh == 0) {
+                    for (int t = 0; t < nt; t++) s = s + lv[t * BM];
+                }
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(bar_tempty(buf));
-                    mbar_arrive(bar_mempty(buf));
-                }
+                if (lane == 0) mbar_arrive(bar_mempty(mb));
             }
-            if (live) {
+            // depth counts of the pair's second warp travel through shared memory
+            if (hh == 1) dsx[q * 32 + lane] = dsum;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            if (hh == 0 && live) {
+                dsum += dsx[q * 32 + lane];
                 if (!p.accumulate_only) {
                     // IF/extended/ExtendedIsolationForestModel.scala:116-119: Float sum / Int, -Float / Float, Math.pow(2, Double)
                     const float e = __fdiv_rn(s, (float)p.total_trees);
@@ -455,6 +524,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 if (p.path_sum) p.path_sum[row] = s;
                 if (p.depth_sum) p.depth_sum[row] = dsum;
             }
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // dsx is free for the next tile
         }
     }
     tc_fence_before();
@@ -467,7 +537,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 
 // ---- per-forest column preparation --------------------------------------------------------------------------------------
 // One warp per accumulator column: power-of-two scaling of the weight row (max |w'| in [0.5, 1)), fp16 hi/lo split,
-// ||w'||_2, the node's offset in its scaled domain and the bound coefficient.
+// ||w'||_2, the node's offset in its scaled domain and the bound of the filter.
 __global__ void ext_tc_prepare_cols(const float *__restrict__ w, const int32_t *__restrict__ col_slot,
                                     const double *__restrict__ col_off, int n_cols, int k, int kp, double ck,
                                     __half *__restrict__ wh, __half *__restrict__ wl, unsigned char *__restrict__ meta,
@@ -511,25 +581,32 @@ __global__ void ext_tc_prepare_cols(const float *__restrict__ w, const int32_t *
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if (lane == 0) {
-        Rec *rec = reinterpret_cast<Rec *>(meta + (size_t)(col / BN) * META_BYTES) + (col % BN);
-        const double offs = ldexp(col_off[col], -e);           // exact unless it leaves the f64 range
-        rec->thr = (float)offs;                                // round to nearest; its error is part of c_k
-        // ||w'||_2 from an f32 sum of <= kp squares: relative error <= kp 2^-24, covered by the 2^-10 inflation
-        const double wn = sqrt((double)sq) * (1.0 + 0x1.0p-10);
-        float ebf = (float)(ck * wn);
-        if ((double)ebf < ck * wn) ebf = nextafterf(ebf, INFINITY);
-        rec->eb = ebf;
+        BlockMeta *M = reinterpret_cast<BlockMeta *>(meta + (size_t)(col / BN) * META_BYTES);
+        const double off = col_off[col];
+        const double offs = ldexp(off, -e);                    // exact unless it leaves the f64 range
+        float thr = (float)offs;                               // round to nearest; its error is part of c_k
+        // an offset beyond the f32 range still decides every ordinary row (|S'| <= k): clamp instead of +-inf so
+        // that inf - inf can never appear in the filter
+        thr = fminf(fmaxf(thr, -3.0e38f), 3.0e38f);
+        // a non-zero offset that rounds to zero would lose its sign for all-zero rows: such forests keep the CUDA-core path
+        if (off != 0.0 && thr == 0.f) bad = true;
+        // ||w'||_2 from an f32 sum of <= kp squares: relative error <= kp 2^-24, covered by the 2^-10 inflation;
+        // the row factor ||x'||_2 is < 1 by construction (ext_tc_prepare_rows)
+        const double bnd = ck * sqrt((double)sq) * (1.0 + 0x1.0p-10);
+        float bf = (float)bnd;
+        if ((double)bf <= bnd) bf = nextafterf(bf, INFINITY);  // strictly above: the filter tests |dlt| - bound >= 0
+        M->ne[col % BN] = make_float2(-thr, bf);
         if (bad) atomicExch(flag, 1);
     }
 }
 
 // ---- per-call row preparation ---------------------------------------------------------------------------------------------
-// 32 rows per CTA staged through shared memory ([row][kp + 1] f32), one warp per 4 rows: power-of-two row scaling
-// (max |x'| in [0.5, 1)), fp16 hi/lo split, ||x'||_2 and a row-major f32 copy for the exact path.
+// 32 rows per CTA staged through shared memory ([row][kp + 1] f32), one warp per 4 rows: power-of-two row scaling that
+// brings ||x'||_2 into [0.5, 1), fp16 hi/lo split, and a row-major f32 copy for the exact path.
 __global__ void __launch_bounds__(256) ext_tc_prepare_rows(const float *__restrict__ X, int64_t n_rows, int d, int64_t ld,
                                                            int layout, int kp, __half *__restrict__ xh,
                                                            __half *__restrict__ xl, float *__restrict__ xr,
-                                                           float *__restrict__ rnorm, float *__restrict__ rscale) {
+                                                           float *__restrict__ rscale, uint8_t *__restrict__ rflag) {
     extern __shared__ float tile[];
     const int pitch = kp + 1;
     const int64_t row0 = (int64_t)blockIdx.x * 32;
@@ -559,32 +636,39 @@ __global__ void __launch_bounds__(256) ext_tc_prepare_rows(const float *__restri
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         bad = __any_sync(0xffffffffu, bad) || (mx > 0.f && mx < 0x1p-60f);
-        int e = 0;
-        if (mx > 0.f && !bad) (void)frexpf(mx, &e);
-        const float sc = ldexpf(1.f, -e);
+        // step 1: max |x| into [0.5, 1); step 2: the norm of that (in [0.5, sqrt(d)]) into [0.5, 1)
+        int e1 = 0;
+        if (mx > 0.f && !bad) (void)frexpf(mx, &e1);
+        const float sc1 = ldexpf(1.f, -e1);
         float sq = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float v = bad ? 0.f : t[c] * sc1;
+            sq = fmaf(v, v, sq);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        int e2 = 0;
+        // f32 sum of <= d squares in [0,1): relative error <= d 2^-24; the 2^-10 inflation keeps the true norm below 2^e2
+        if (sq > 0.f) (void)frexpf(sqrtf(sq) * (1.0f + 0x1.0p-10f), &e2);
+        const float sc = ldexpf(1.f, -(e1 + e2));
         __half *oh = xh + (size_t)row * kp, *ol = xl + (size_t)row * kp;
         float *of = xr + (size_t)row * kp;
         for (int c = lane; c < kp; c += 32) {
             const float x = c < d ? t[c] : 0.f;
             float hi = 0.f, lo = 0.f;
             if (!bad) {
-                const float v = x * sc;
+                const float v = x * sc;        // exact power-of-two scaling (tiny elements may flush: absolute error < 2^-126)
                 const __half h = __float2half_rn(v);
                 hi = __half2float(h);
                 lo = v - hi;
-                sq = fmaf(v, v, sq);
             }
             oh[c] = __float2half_rn(hi);
             ol[c] = __float2half_rn(lo);
             of[c] = x;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         if (lane == 0) {
-            // f32 sum of <= kp squares in [0,1): relative error <= kp 2^-24; inflate by 2^-10
-            rnorm[row] = bad ? __int_as_float(0x7f800000) : sqrtf(sq) * (1.0f + 0x1.0p-10f);
-            rscale[row] = sc;
+            rscale[row] = bad ? 1.f : sc;
+            rflag[row] = bad ? 2 : (mx == 0.f ? 1 : 0);
         }
     }
 }
@@ -632,8 +716,9 @@ int make_tc_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int32_t kp, in
 }
 
 // Bound constant of the tensor-core filter (scaled domain):
-//   representation   3 * 2^-22 + 4.004 * sqrt(k) * 2^-25   (two-term fp16 splits of both operands, dropped lo*lo term,
-//                                                            absolute 2^-25 resolution of fp16 below 2^-14)
+//   representation   3 * 2^-22 + 4.1 * sqrt(k) * 2^-25     (two-term fp16 splits of both operands, dropped lo*lo term,
+//                                                            absolute 2^-25 resolution of fp16 below 2^-14; both
+//                                                            ||x'|| and ||w'|| are >= 0.4995)
 //   reference        2^-23                                   ((u + k 2^-53)(1 + u) of the f32 products / f64 sum, and the
 //                                                            f32 rounding of the scaled offset)
 //   accumulation     nsteps * u_acc * 1.01                   (nsteps = 3 kp / 16 MMA accumulation steps, each assumed
@@ -643,7 +728,7 @@ int make_tc_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int32_t kp, in
 double tc_bound_constant(int k, int kp) {
     static const double u_acc = getenv("IFB_TC_UACC_LOG2") ? std::ldexp(1.0, atoi(getenv("IFB_TC_UACC_LOG2"))) : 0x1.0p-22;
     const double nsteps = 3.0 * (double)(kp / 16);
-    double ck = 3.0 * 0x1.0p-22 + 4.004 * std::sqrt((double)k) * 0x1.0p-25 + 0x1.0p-23 + nsteps * u_acc * 1.01;
+    double ck = 3.0 * 0x1.0p-22 + 4.1 * std::sqrt((double)k) * 0x1.0p-25 + 0x1.0p-23 + nsteps * u_acc * 1.01;
     return ck * (1.0 + 0x1.0p-12);
 }
 
@@ -665,63 +750,95 @@ int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const 
         BlockMeta &m = metas.back();
         std::memset(&m, 0, sizeof m);
         for (int i = 0; i < BN; i++) {
-            m.rec[i].thr = 0.f;
-            m.rec[i].eb = 0.f;
-            m.rec[i].refs = 0x80008000u;
-            m.rec[i].slot = -1;
+            m.ne[i] = make_float2(0.f, 0.f);
+            m.refs[i] = 0x80008000u;
+            m.slot[i] = -1;
         }
         m.tree0 = tree0;
         col_slot.resize(metas.size() * BN, -1);
         col_off.resize(metas.size() * BN, 0.0);
     };
-    new_block(0);
-    int half = 0, used = 0, n_leaves = 0;   // state of the block being filled
-    std::vector<int32_t> ref_of;
+    // internal-node / leaf counts per tree
+    std::vector<int> tm(T), tl(T);
     for (int t = 0; t < T; t++) {
         const int64_t base = f->node_off[t];
         const int n = f->node_off[t + 1] - f->node_off[t];
         int m = 0;
         for (int q = 0; q < n; q++) m += child[base + q] >= 0;
-        if (m > HALF) return IFB_OK;   // a tree wider than the spill unit: the forest keeps the CUDA-core kernels
-        const int nl = n - m;
-        BlockMeta *M = &metas.back();
-        if (used + m > HALF && half == 0) {
-            half = 1;
-            used = 0;
+        if (m > MAX_TREE_COLS) return IFB_OK;   // a tree wider than one warp's span: the forest keeps the CUDA-core kernels
+        tm[t] = m;
+        tl[t] = n - m;
+    }
+    std::vector<int32_t> ref_of;
+    for (int ta = 0; ta < T;) {
+        // greedily take consecutive trees, then split them into two consecutive groups (one per warp of a pair) whose
+        // column spans, counted from a 32-aligned base, fit MAX_GROUP_SPAN; balance the two spans
+        int cnt = 0, cols = 0, leaves = 0;
+        while (ta + cnt < T && cnt < MAX_TREES_PER_BLOCK && cols + tm[ta + cnt] <= BN &&
+               leaves + tl[ta + cnt] <= MAX_LEAVES_PER_BLOCK) {
+            cols += tm[ta + cnt];
+            leaves += tl[ta + cnt];
+            cnt++;
         }
-        if (used + m > HALF || M->n_trees == MAX_TREES_PER_BLOCK || n_leaves + nl > MAX_LEAVES_PER_BLOCK) {
-            new_block(t);
-            M = &metas.back();
-            half = 0;
-            used = 0;
-            n_leaves = 0;
-        }
-        if (half == 0) M->n_trees_half0++;
-        const int blk = (int)metas.size() - 1;
-        // references of the tree's nodes: internal -> column, leaf -> leaf slot
-        ref_of.assign(n, 0);
-        int ci = 0, li = 0;
-        for (int q = 0; q < n; q++) {
-            if (child[base + q] >= 0) ref_of[q] = half * HALF + used + ci++;
-            else ref_of[q] = 0x8000 | (n_leaves + li++);
-        }
-        for (int q = 0; q < n; q++) {
-            const int64_t g = base + q;
-            if (child[g] >= 0) {
-                const int col = ref_of[q];
-                Rec &r = M->rec[col];
-                r.refs = (uint32_t)ref_of[child[g]] | ((uint32_t)ref_of[child[g] + 1] << 16);
-                r.slot = hp[g];
-                col_slot[(size_t)blk * BN + col] = hp[g];
-                col_off[(size_t)blk * BN + col] = off[g];
-            } else {
-                M->leafv[ref_of[q] & 0x7FFF] = leaf[g];
+        int best_s = -1, best_c0 = 0;
+        while (true) {
+            int best_cost = 1 << 30;
+            int c0 = 0;
+            for (int sidx = 0; sidx <= cnt; sidx++) {   // group 0 = trees [ta, ta+sidx)
+                const int span0 = c0, span1 = cols - (c0 / 32) * 32;
+                if (span0 <= MAX_GROUP_SPAN && (sidx == cnt || span1 <= MAX_GROUP_SPAN)) {
+                    const int cost = std::max((span0 + 31) / 32, sidx == cnt ? 0 : (span1 + 31) / 32);
+                    if (cost < best_cost) {
+                        best_cost = cost;
+                        best_s = sidx;
+                        best_c0 = c0;
+                    }
+                }
+                if (sidx < cnt) c0 += tm[ta + sidx];
             }
+            if (best_s >= 0 || cnt <= 1) break;
+            cnt--;   // no feasible split: drop the last tree and retry
+            cols -= tm[ta + cnt];
+            leaves -= tl[ta + cnt];
         }
-        M->root[M->n_trees++] = (uint16_t)ref_of[0];
-        used += m;
-        n_leaves += nl;
-        M->ncols_half[half] = used;
+        if (best_s < 0) return IFB_OK;
+        new_block(ta);
+        BlockMeta *M = &metas.back();
+        const int blk = (int)metas.size() - 1;
+        M->n_trees = cnt;
+        M->n_trees_g0 = best_s;
+        M->gbase[0] = 0;
+        M->gchunks[0] = (best_c0 + 31) / 32;
+        M->gbase[1] = (best_c0 / 32) * 32;
+        M->gchunks[1] = best_s == cnt ? 0 : (cols - M->gbase[1] + 31) / 32;
+        int used = 0, n_leaves = 0;
+        for (int i = 0; i < cnt; i++) {
+            const int t = ta + i;
+            const int64_t base = f->node_off[t];
+            const int n = f->node_off[t + 1] - f->node_off[t];
+            ref_of.assign(n, 0);
+            int ci = 0, li = 0;
+            for (int q = 0; q < n; q++) {
+                if (child[base + q] >= 0) ref_of[q] = used + ci++;
+                else ref_of[q] = 0x8000 | (n_leaves + li++);
+            }
+            for (int q = 0; q < n; q++) {
+                const int64_t g = base + q;
+                if (child[g] >= 0) {
+                    const int col = ref_of[q];
+                    M->refs[col] = (uint32_t)ref_of[child[g]] | ((uint32_t)ref_of[child[g] + 1] << 16);
+                    M->slot[col] = hp[g];
+                    col_slot[(size_t)blk * BN + col] = hp[g];
+                    col_off[(size_t)blk * BN + col] = off[g];
+                } else {
+                    M->leafv[ref_of[q] & 0x7FFF] = leaf[g];
+                }
+            }
+            M->root[i] = (uint16_t)ref_of[0];
+            used += tm[t];
+            n_leaves += tl[t];
+        }
+        ta += cnt;
     }
     const int NB = (int)metas.size();
     const size_t ncols = (size_t)NB * BN;
@@ -786,7 +903,8 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     unsigned char *a = reinterpret_cast<unsigned char *>(scr.p);
     __half *xh = reinterpret_cast<__half *>(a), *xl = reinterpret_cast<__half *>(a + b_h);
     float *xr = reinterpret_cast<float *>(a + 2 * b_h);
-    float *rnorm = reinterpret_cast<float *>(a + 2 * b_h + b_f), *rscale = reinterpret_cast<float *>(a + 2 * b_h + b_f + b_n);
+    float *rscale = reinterpret_cast<float *>(a + 2 * b_h + b_f);
+    uint8_t *rflag = reinterpret_cast<uint8_t *>(a + 2 * b_h + b_f + b_n);
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(a + 2 * b_h + b_f + 2 * b_n);
     if (want_stats) IFB_CUDA(cudaMemsetAsync(stats, 0, 8, stream));
 
@@ -796,7 +914,8 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     rc = make_tc_tmap(&m_wl, f->d_tc_wl, (int64_t)f->tc_blocks * BN, kp, BN);
     if (rc) return rc;
     const int sms = device_sm_count(f->device);
-    IFB_CUDA(cudaFuncSetAttribute(score_ext_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    IFB_CUDA(cudaFuncSetAttribute(score_ext_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    IFB_CUDA(cudaFuncSetAttribute(score_ext_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     const size_t prep_smem = (size_t)32 * (kp + 1) * 4;
     IFB_CUDA(cudaFuncSetAttribute(ext_tc_prepare_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
 
@@ -804,7 +923,7 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
         const int64_t rows = std::min<int64_t>(chunk, n_rows - r0);
         const float *Xc = layout == IFB_COL_MAJOR ? X + r0 : X + r0 * ld;
         ext_tc_prepare_rows<<<(unsigned)((rows + 31) / 32), 256, prep_smem, stream>>>(Xc, rows, d, ld, layout, kp, xh, xl, xr,
-                                                                                     rnorm, rscale);
+                                                                                     rscale, rflag);
         IFB_CUDA(cudaGetLastError());
         count_launch();
         CUtensorMap m_xh, m_xl;
@@ -818,8 +937,8 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
         p.kp = kp;
         p.k = f->tc_k;
         p.n_rows = rows;
-        p.rnorm = rnorm;
         p.rscale = rscale;
+        p.rflag = rflag;
         p.xr = xr;
         p.w = f->d_ext_w;
         p.wabs = f->d_ext_wabs;
@@ -836,7 +955,8 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
         p.stats = want_stats ? stats : nullptr;
         const int64_t n_tiles = (rows + BM - 1) / BM;
         const int grid = (int)std::min<int64_t>(n_tiles, sms);
-        score_ext_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(m_xh, m_xl, m_wh, m_wl, p);
+        if (eb_scale != 1.0f) score_ext_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(m_xh, m_xl, m_wh, m_wl, p);
+        else score_ext_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(m_xh, m_xl, m_wh, m_wl, p);
         IFB_CUDA(cudaGetLastError());
         count_launch();
     }

@@ -92,6 +92,47 @@ def score_tree_sharded(local_forest, X, total_num_trees: int, num_samples: int, 
     return (scores, dsum, psum) if want_depth else scores
 
 
+def hybrid_groups(world: int, tree_shards: int):
+    """Hybrid rows x trees layout: ranks [g*S, (g+1)*S) form row group g and split the ensemble S ways.
+
+    Every rank must call this (torch.distributed.new_group is collective); returns (my group, row group index,
+    number of row groups).  S == world is pure tree sharding, S == 1 is the collective-free row sharding."""
+    import torch.distributed as dist
+
+    assert world % tree_shards == 0, (world, tree_shards)
+    rank = dist.get_rank()
+    mine = None
+    for g in range(world // tree_shards):
+        grp = dist.new_group(list(range(g * tree_shards, (g + 1) * tree_shards)))
+        if rank // tree_shards == g:
+            mine = grp
+    return mine, rank // tree_shards, world // tree_shards
+
+
+def score_tree_sharded_rs(local_forest, X, total_num_trees: int, num_samples: int, group=None, psum=None, out=None,
+                          scores=None):
+    """Tree-sharded transform with a REDUCE-SCATTER: every rank of `group` ends up with the scores of its own
+    contiguous row slice only (rows are padded to a multiple of the group size).  Returns (scores_local, r0, r1)."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _native as nat
+
+    n = X.shape[0]
+    S, r = dist.get_world_size(group), dist.get_rank(group)
+    per = (n + S - 1) // S
+    if psum is None:
+        psum = torch.empty(per * S, dtype=torch.float32, device=X.device)
+    psum.zero_()
+    local_forest.score_partial_device(X, psum[:n])
+    if out is None:
+        out = torch.empty(per, dtype=torch.float32, device=X.device)
+    dist.reduce_scatter_tensor(out, psum, group=group)
+    r0, r1 = min(n, r * per), min(n, (r + 1) * per)
+    scores = nat.finalize_scores_device(out[: r1 - r0], total_num_trees, num_samples, scores=scores)
+    return scores, r0, r1
+
+
 class ScatterContext:
     """Peer-memory buffers for the FUSED tree-sharded transform (include/ifb200.h: ifb_score_scatter_device).
 

@@ -128,3 +128,32 @@ def test_fit_argument_errors(nat):
         nat.fit_device(X, nat.FitParams(10, 50, 5, 0, 1, 1, -1, 0, 0))
     with pytest.raises(ValueError, match=r"extensionLevel given invalid value 4, but must be in \[0, 3\]"):
         nat.fit_device(X, nat.FitParams(10, 50, 4, 0, 1, 1, 4, 0, 0))
+
+
+def test_degenerate_splits_are_an_error_not_a_memory_fault(nat, oracle):
+    """A column holding both -inf and +inf gives NaN / infinite split values: every row goes right and a 0-row left leaf
+    appears level after level.  The reference fails the ExternalNode requirement (numInstances > 0, IF/Nodes.scala:27-31);
+    the builder must report an error and must not write past the tree's slice of the node tables."""
+    X = synth_mixture(4096, 4, 3)
+    X[::2, 1] = -np.inf
+    X[1::2, 1] = np.inf
+    with pytest.raises((ValueError, RuntimeError)):
+        fit_gpu(nat, X, 16, 256)
+    # the library is still healthy afterwards
+    ok = synth_mixture(4096, 4, 3)
+    assert_tables_equal(fit_gpu(nat, ok, 8, 256).export(), oracle.fit_forest(ok, 8, 256, random_seed=1))
+
+
+def test_fit_host_reads_only_the_addressed_extent(nat, oracle):
+    """ifb_fit_host on strided views (an F-order slice base[k:k+n], a C-order column slice): only (d-1)*ld + n_rows resp.
+    (n_rows-1)*ld + d elements belong to the caller."""
+    n, d = 3000, 7
+    X = synth_mixture(n, d, 21)
+    ref = oracle.fit_forest(X, 10, 256, random_seed=1)
+    prm = nat.FitParams(10, 256, d, 0, 1, 1, -1, 0, 0)
+    base = np.asfortranarray(np.concatenate([np.full((5, d), np.nan, np.float32), X]))
+    view = base[5:5 + n]                       # column-major, ld = n + 5, ends exactly at the allocation's end
+    assert_tables_equal(nat.fit_host(view, prm).export(), ref)
+    wide = np.full((n, d + 3), np.nan, np.float32)
+    wide[:, :d] = X
+    assert_tables_equal(nat.fit_host(wide[:, :d], prm).export(), ref)   # row-major, ld = d + 3

@@ -18,7 +18,8 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-for ext, d, T, n in ((-1, 32, 100, 2_000_000), (15, 16, 40, 300_000)):
+comm = None
+for ext, d, T, n in ((-1, 32, 100, 2_000_000), (15, 16, 40, 300_000), (63, 64, 24, 200_000)):
     gen = torch.Generator(device=dev).manual_seed(99)
     X = torch.randn(d, n, device=dev, generator=gen).t()            # identical on every rank
     prm = nat.FitParams(T, 256, d, 0, 1, 1, ext, 0, 0)
@@ -44,8 +45,38 @@ for ext, d, T, n in ((-1, 32, 100, 2_000_000), (15, 16, 40, 300_000)):
         ctx.close()
         if rank == 0:
             print(f"fused scatter ok: max rel {relf:.2e}", flush=True)
+    # the same layout with the collective inside libifb200.so (ifb_comm_init / ifb_score_sharded: what a JVM would bind)
+    if comm is None:
+        uid = [nat.NativeComm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = nat.NativeComm(local, world, rank, uid[0])
+    s_lib, b0, b1 = comm.score_sharded(local_forest, X, T, nat.SHARD_ALLREDUCE)
+    torch.cuda.synchronize()
+    rel_ar = float(((s_lib - s_ref).abs() / s_ref).max())
+    assert (b0, b1) == (0, n) and rel_ar < 1e-6, rel_ar
+    s_rs, b0, b1 = comm.score_sharded(local_forest, X, T, nat.SHARD_REDUCE_SCATTER)
+    torch.cuda.synchronize()
+    rel_rs = float(((s_rs - s_ref[b0:b1]).abs() / s_ref[b0:b1]).max())
+    assert rel_rs < 1e-6, rel_rs
+    if rank == 0:
+        print(f"ifb_score_sharded ok: all-reduce max rel {rel_ar:.2e}, reduce-scatter slice [{b0},{b1}) max rel {rel_rs:.2e}",
+              flush=True)
+    # hybrid rows x trees: groups of 2 tree shards, each group owns a contiguous row range
+    if world % 2 == 0 and world > 2:
+        grp, g, G = D.hybrid_groups(world, 2)
+        g0, g1 = D.row_shard(n, g, G)
+        t0, t1 = D.tree_shard(T, rank % 2, 2)
+        lf = nat.fit_device(X, nat.FitParams(T, 256, d, 0, 1, 1, ext, t0, t1))
+        s_h, h0, h1 = D.score_tree_sharded_rs(lf, X[g0:g1], T, 256, group=grp)
+        torch.cuda.synchronize()
+        rel_h = float(((s_h - s_ref[g0 + h0:g0 + h1]).abs() / s_ref[g0 + h0:g0 + h1]).max())
+        assert rel_h < 1e-6, rel_h
+        if rank == 0:
+            print(f"hybrid {G}x2 reduce-scatter ok: max rel {rel_h:.2e}", flush=True)
     s_rows = full.score_device(X[r0:r1])
     assert torch.equal(s_rows, s_ref[r0:r1]), "row sharding must be bit-identical"
     if rank == 0:
         print(f"multi-gpu check ok: world={world} ext={ext} d={d} T={T} n={n} tree-shard max rel {rel:.2e}", flush=True)
+if comm is not None:
+    comm.close()
 dist.destroy_process_group()
