@@ -239,6 +239,8 @@ IFB_API int ifb_fit_host(int32_t device, const float *X, int64_t n_rows, int32_t
 /* returns (IF/core/SharedTrainLogic.scala:191-198): element of 1-based rank ceil(q*n) of the sorted  */
 /* scores.  Also returns the observed contamination  #(score >= value)/n  (:211-213).                */
 /* ---------------------------------------------------------------------------------------------- */
+/* The result is returned in HOST memory, so the call enqueues its 8 radix passes on `stream` and then blocks until they
+ * have finished (the reference's approxQuantile is an action as well). */
 IFB_API int ifb_quantile_device(int32_t device, const double *scores, int64_t n_rows, double q, double *value,
                                 double *observed_fraction_ge, void *stream);
 

@@ -9,6 +9,18 @@
 namespace ifb {
 
 namespace {
+// SM count of the current device (grids are sized in multiples of it), cached per device
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return device_sm_count(dev);
+    if (!cached[dev]) cached[dev] = device_sm_count(dev);
+    return cached[dev];
+}
+}  // namespace
+
+namespace {
 
 // IF/IsolationForestModel.scala:137-138 applied to an already reduced f32 path-length sum.
 __global__ void finalize_kernel(const float *__restrict__ path_sum, int64_t n, float total_trees, float avg_path,
@@ -151,7 +163,7 @@ __global__ void count_ge_kernel(const double *__restrict__ v, int64_t n, const S
 int launch_finalize(const float *path_sum, int64_t n_rows, int32_t total_trees, float avg_path, double *scores,
                     cudaStream_t stream) {
     if (n_rows == 0) return IFB_OK;
-    const int grid = (int)std::min<int64_t>((n_rows + 255) / 256, 148 * 16);
+    const int grid = (int)std::min<int64_t>((n_rows + 255) / 256, sm_count() * 16);
     finalize_kernel<<<grid, 256, 0, stream>>>(path_sum, n_rows, (float)total_trees, avg_path, scores);
     IFB_CUDA(cudaGetLastError());
     count_launch();
@@ -161,7 +173,7 @@ int launch_finalize(const float *path_sum, int64_t n_rows, int32_t total_trees, 
 int launch_finalize_gathered(const float *partials, int32_t world, int64_t rows_local, int32_t total_trees, float avg_path,
                              double *scores, cudaStream_t stream) {
     if (rows_local == 0) return IFB_OK;
-    const int grid = (int)std::min<int64_t>((rows_local + 255) / 256, 148 * 16);
+    const int grid = (int)std::min<int64_t>((rows_local + 255) / 256, sm_count() * 16);
     finalize_gathered_kernel<<<grid, 256, 0, stream>>>(partials, world, rows_local, (float)total_trees, avg_path, scores);
     IFB_CUDA(cudaGetLastError());
     count_launch();
@@ -185,7 +197,7 @@ int launch_peer_wait(int world, const uint32_t *local_flags, uint32_t epoch, cud
 
 int launch_predict(const double *scores, int64_t n_rows, double threshold, double *labels, cudaStream_t stream) {
     if (n_rows == 0) return IFB_OK;
-    const int grid = (int)std::min<int64_t>((n_rows + 255) / 256, 148 * 16);
+    const int grid = (int)std::min<int64_t>((n_rows + 255) / 256, sm_count() * 16);
     predict_kernel<<<grid, 256, 0, stream>>>(scores, n_rows, threshold, labels);
     IFB_CUDA(cudaGetLastError());
     count_launch();
@@ -196,7 +208,7 @@ int launch_transpose(const float *in, int64_t n, int32_t d, int64_t ld_in, float
                      cudaStream_t stream) {
     if (n == 0) return IFB_OK;
     const int64_t tiles = ((n + 31) / 32) * ((d + 31) / 32);
-    const int grid = (int)std::min<int64_t>(tiles, 148 * 32);
+    const int grid = (int)std::min<int64_t>(tiles, sm_count() * 32);
     transpose_rm_to_cm_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, n, d, ld_in, out, ld_out);
     IFB_CUDA(cudaGetLastError());
     count_launch();
@@ -211,7 +223,7 @@ int launch_select(const double *scores, int64_t n, int64_t rank0, double *value,
     IFB_CUDA(cudaMemsetAsync(st, 0, sizeof(SelectState), stream));
     unsigned long long r = (unsigned long long)rank0;
     IFB_CUDA(cudaMemcpyAsync(&st->rank, &r, sizeof r, cudaMemcpyHostToDevice, stream));
-    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, sm_count() * 8);
     for (int shift = 56; shift >= 0; shift -= 8) {
         select_hist_kernel<<<grid, 256, 0, stream>>>(scores, n, shift, st);
         select_pick_kernel<<<1, 32, 0, stream>>>(shift, st);

@@ -127,15 +127,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Bounded wait: a lost transaction / bad descriptor must surface as a launch failure, never as a hung GPU
 // (wall-clock bound of ~4 s on %globaltimer; the longest legitimate wait is one block of MMAs, tens of microseconds).
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    // the suspend-time hint lets the hardware park the thread until the phase completes (or the hint expires) instead
+    // of returning early: a waiting role then costs no issue slots of the scheduler it shares with the epilogue warps
     uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(200000u)
         : "memory");
     return done != 0;
 }
@@ -144,22 +146,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (uint32_t spin = 1;; ++spin) {
-        if (mbar_try(bar, parity)) return;
-        if ((spin & 1023u) == 0) {
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ull) __trap();
-        }
-    }
-}
-// Same, for the single-lane producer / MMA roles: they have slack, so they back off between polls instead of taking
-// issue slots from the epilogue warps that share their scheduler.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    if (mbar_try(bar, parity)) return;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (uint32_t spin = 1;; ++spin) {
-        __nanosleep(64);
         if (mbar_try(bar, parity)) return;
         if ((spin & 1023u) == 0) {
             unsigned long long t1;
@@ -307,12 +293,12 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int b = 0; b < NB; b++, it++) {
                     const int mb = (int)(it % META_RING);
-                    mbar_wait_relaxed(bar_mempty(mb), ((it / META_RING) & 1u) ^ 1u);
+                    mbar_wait(bar_mempty(mb), ((it / META_RING) & 1u) ^ 1u);
                     mbar_expect_tx(bar_mfull(mb), META_BYTES);
                     bulk_g2s(base + OFF_META + (uint32_t)mb * META_BYTES, p.meta + (size_t)b * META_BYTES, META_BYTES,
                              bar_mfull(mb));
                     for (int kc = 0; kc < KC; kc++) {
-                        mbar_wait_relaxed(bar_empty(stage), phase ^ 1u);
+                        mbar_wait(bar_empty(stage), phase ^ 1u);
                         const uint32_t st = base + OFF_STAGES + (uint32_t)stage * STAGE_BYTES;
                         mbar_expect_tx(bar_full(stage), STAGE_BYTES);
                         tma_load_2d(st, &map_xh, kc * BK, (int32_t)(tile * BM), bar_full(stage));
