@@ -847,7 +847,10 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     const size_t per_node = 4 + 4 + 8 + (ext ? 8 + 4 : 4 + 8);
     // hyperplane rows of all trees ride in the same batch when they are small enough to stage whole
     const size_t hp_elems = ext ? T * (size_t)cap_internal * k : 0;
-    const bool hp_staged = ext && hp_elems * 8 <= ((size_t)64 << 20);
+    // wide dense hyperplanes (k == d > 64: indices are 0..k-1 by construction) never leave the device: the forest
+    // gathers its scoring tables from the builder's weight array directly (forest.cu::create_extended_from_device)
+    const bool hp_on_device = ext && k == d && k > 64 && std::getenv("IFB_FIT_HOST_HP") == nullptr;
+    const bool hp_staged = ext && !hp_on_device && hp_elems * 8 <= ((size_t)64 << 20);
     const size_t stage_bytes = T * 8 + T * (size_t)cap * per_node + (hp_staged ? hp_elems * 8 + 16 : 0) + 64;
     if ((rc = g_stage.reserve(stage_bytes))) return rc;
     unsigned char *sp = (unsigned char *)g_stage.p;
@@ -906,6 +909,7 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     }
     std::vector<int32_t> hidx_t;
     std::vector<float> hw_t;
+    std::vector<int64_t> src_row(hp_on_device ? (size_t)total : 0, -1);
     for (int t = 0; t < ntrees; t++) {
         const int64_t src = (int64_t)t * cap, dst = node_off[t];
         const int nn = n_nodes[t];
@@ -917,6 +921,11 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
             std::memcpy(&c_thr[dst], &thr[src], nn * 8);
         } else {
             std::memcpy(&c_off[dst], &off[src], nn * 8);
+            if (hp_on_device) {
+                for (int i = 0; i < nn; i++)
+                    if (left[src + i] != -1) src_row[(size_t)(dst + i)] = (int64_t)t * cap_internal + slot[src + i];
+                continue;
+            }
             const int ni = n_int[t];
             const int32_t *hidx_p;
             const float *hw_p;
@@ -947,6 +956,15 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     }
     stage_lock.unlock();
     if (timing) std::fprintf(stderr, "[ifb fit] tables on the host and compacted at %.3f ms\n", ms_since(t_start));
+    if (hp_on_device) {
+        DeviceHyperplanes dh;
+        dh.w = p.hp_w;
+        dh.src_row = src_row.data();
+        rc = create_extended_from_device(device, ntrees, node_off.data(), c_left.data(), c_right.data(), c_ninst.data(),
+                                         c_off.data(), k, dh, n, d, out);
+        if (timing) std::fprintf(stderr, "[ifb fit] forest handle (device-resident hyperplanes) created at %.3f ms\n", ms_since(t_start));
+        return rc;
+    }
     rc = ext ? ifb_forest_create_extended(device, ntrees, node_off.data(), c_left.data(), c_right.data(), c_ninst.data(),
                                           c_off.data(), hp_off.data(), hp_idx.data(), hp_w.data(), n, d, out)
              : ifb_forest_create_standard(device, ntrees, node_off.data(), c_left.data(), c_right.data(), c_feat.data(),

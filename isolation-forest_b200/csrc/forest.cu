@@ -146,7 +146,52 @@ int build_standard_tables(ifb_forest *f) {
     return IFB_OK;
 }
 
-int build_extended_tables(ifb_forest *f) {
+// ---- device-resident hyperplanes (forests fitted on the device, k == d > 64) ---------------------------------------
+namespace {
+// slot s of the scoring layout <- row slot_src[s] of the builder's weight array (one warp per slot); also the slot's
+// sum |w| and ||w||_2 (f64, the bounds of the exact / f32 tiers) and the "weights are f32-tier safe" flag
+__global__ void ext_gather_weights_kernel(const float *__restrict__ src, const int64_t *__restrict__ slot_src, int64_t n_slots,
+                                          int k, float *__restrict__ w, double *__restrict__ wabs, double *__restrict__ wnorm,
+                                          int32_t *__restrict__ unsafe) {
+    const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= n_slots) return;
+    const float *in = src + slot_src[s] * k;
+    float *out = w + s * k;
+    double a = 0.0, q = 0.0;
+    bool bad = false;
+    for (int i = lane; i < k; i += 32) {
+        const float v = in[i];
+        out[i] = v;
+        a += fabs((double)v);
+        q += (double)v * (double)v;
+        bad = bad || !(fabsf(v) <= 0x1p40f);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        // lane-parallel f64 sums differ from a sequential sum by <= k 2^-53 relative: covered by the inflations
+        wabs[s] = a * 1.0000001;
+        wnorm[s] = sqrt(q) * 1.0000002;
+        if (bad) atomicExch(unsafe, 1);
+    }
+}
+__global__ void ext_patch_wide_nodes_kernel(WideNode *nodes, int64_t n_nodes, const double *__restrict__ wnorm) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n_nodes) return;
+    const int32_t slot = nodes[g].slot;
+    if (slot < 0) return;
+    const double v = wnorm[slot];
+    float wf = (float)v;
+    if ((double)wf < v) wf = nextafterf(wf, INFINITY);
+    nodes[g].wnorm = wf;
+}
+}  // namespace
+
+int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
     const int T = f->num_trees;
     const int64_t total = f->node_off[T];
     const int k = f->max_nnz;
@@ -156,8 +201,11 @@ int build_extended_tables(ifb_forest *f) {
     std::vector<int64_t> tree_node(f->node_off.begin(), f->node_off.end());
     int64_t internal = 0;
     for (int64_t g = 0; g < total; g++) internal += (f->left[g] != -1);
-    std::vector<float> w((size_t)internal * k, 0.f);
-    std::vector<int32_t> idx((size_t)internal * k, 0);
+    // weights that already live on the device are gathered there (dev != nullptr): no host copy of w / idx
+    std::vector<float> w(dev ? 0 : (size_t)internal * k, 0.f);
+    std::vector<int32_t> idx(dev ? 0 : (size_t)internal * k, 0);
+    std::vector<int64_t> slot_src(dev ? (size_t)internal : 0, 0);
+    if (dev) f->lazy_slot_of_node.assign((size_t)total, -1);
     bool identity = true;
     f->max_depth = 0;
     std::vector<int32_t> order, dep, pos;
@@ -178,6 +226,13 @@ int build_extended_tables(ifb_forest *f) {
                 off[g] = f->offset[src];
                 child[g] = pos[f->left[src]];
                 hp[g] = (int32_t)slot;
+                if (dev) {
+                    len[g] = k;
+                    slot_src[(size_t)slot] = dev->src_row[src];
+                    f->lazy_slot_of_node[(size_t)src] = (int32_t)slot;
+                    slot++;
+                    continue;
+                }
                 const int64_t b = f->hp_off[src], e = f->hp_off[src + 1];
                 len[g] = (int32_t)(e - b);
                 // Rows narrower than k are padded (index of the last term, weight 0); kernels stop at len.
@@ -227,7 +282,7 @@ int build_extended_tables(ifb_forest *f) {
     std::vector<unsigned char> blob;
     std::vector<int64_t> boff(T + 1, 0);
     int rc;
-    if ((rc = up((void **)&f->d_ext_w, w.data(), w.size() * 4))) return rc;
+    if ((rc = up((void **)&f->d_ext_w, dev ? nullptr : w.data(), (size_t)internal * k * 4))) return rc;
     if (!f->ext_dense_identity)
         if ((rc = up((void **)&f->d_ext_idx, idx.data(), idx.size() * 4))) return rc;
     if ((rc = up((void **)&f->d_ext_off, off.data(), off.size() * 8))) return rc;
@@ -236,7 +291,7 @@ int build_extended_tables(ifb_forest *f) {
     if ((rc = up((void **)&f->d_ext_hp, hp.data(), hp.size() * 4))) return rc;
     if ((rc = up((void **)&f->d_ext_len, len.data(), len.size() * 4))) return rc;
     {
-        for (int64_t sl = 0; sl < internal; sl++) {
+        for (int64_t sl = 0; sl < (dev ? 0 : internal); sl++) {
             double a = 0.0, q = 0.0;
             for (int i = 0; i < k; i++) {
                 const double v = (double)w[(size_t)sl * k + i];
@@ -246,8 +301,8 @@ int build_extended_tables(ifb_forest *f) {
             wabs[(size_t)sl] = a;
             wnorm[(size_t)sl] = std::sqrt(q) * 1.0000001;
         }
-        if ((rc = up((void **)&f->d_ext_wabs, wabs.data(), wabs.size() * 8))) return rc;
-        if ((rc = up((void **)&f->d_ext_wnorm, wnorm.data(), wnorm.size() * 8))) return rc;
+        if ((rc = up((void **)&f->d_ext_wabs, dev ? nullptr : wabs.data(), wabs.size() * 8))) return rc;
+        if ((rc = up((void **)&f->d_ext_wnorm, dev ? nullptr : wnorm.data(), wnorm.size() * 8))) return rc;
         for (int t = 0; t < T; t++) {
             const int64_t base = f->node_off[t];
             const int n = f->node_off[t + 1] - f->node_off[t];
@@ -264,6 +319,7 @@ int build_extended_tables(ifb_forest *f) {
                 if (child[g] >= 0) {
                     r.slot_l = hp[base + child[g]];
                     r.slot_r = hp[base + child[g] + 1];
+                    if (dev) continue;   // wnorm is patched on the device once the weights have been gathered
                     float wf = (float)wnorm[(size_t)hp[g]];
                     if ((double)wf < wnorm[(size_t)hp[g]]) wf = std::nextafterf(wf, INFINITY);
                     r.wnorm = wf;
@@ -335,6 +391,25 @@ int build_extended_tables(ifb_forest *f) {
     }
     rc = commit();
     if (rc) return rc;
+    if (dev && internal > 0) {
+        int64_t *d_src = nullptr;
+        int32_t *d_flag = nullptr;
+        IFB_CUDA(cudaMalloc((void **)&d_src, (size_t)internal * 8 + 16));
+        d_flag = reinterpret_cast<int32_t *>(d_src + internal);
+        IFB_CUDA(cudaMemcpyAsync(d_src, slot_src.data(), (size_t)internal * 8, cudaMemcpyHostToDevice, 0));
+        IFB_CUDA(cudaMemsetAsync(d_flag, 0, 4, 0));
+        ext_gather_weights_kernel<<<(unsigned)((internal + 7) / 8), 256>>>(dev->w, d_src, internal, k, f->d_ext_w, f->d_ext_wabs,
+                                                                            f->d_ext_wnorm, d_flag);
+        ext_patch_wide_nodes_kernel<<<(unsigned)((total + 255) / 256), 256>>>(reinterpret_cast<WideNode *>(f->d_ext_wide_nodes),
+                                                                                total, f->d_ext_wnorm);
+        count_launch(2);
+        int32_t unsafe = 0;
+        cudaError_t e = cudaMemcpy(&unsafe, d_flag, 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_src);
+        IFB_CUDA(e);
+        IFB_CUDA(cudaGetLastError());
+        f->ext_w_safe = unsafe == 0;
+    }
     // tensor-core layout (fully-extended forests; a forest that does not qualify simply keeps tc_ok = false)
     if (f->ext_dense_identity && getenv("IFB_EXT_NO_TC") == nullptr) {
         rc = build_ext_tc_tables(f, child, hp, leaf, off);
@@ -387,9 +462,12 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
     const int nCand = try1024 ? 9 : 8;
     static const bool single_ok = getenv("IFB_STD_NO_SINGLE_STAGE") == nullptr;
     int R = 0, S = 2;
-    for (int ci = 0; ci < nCand; ci++) {   // pass 1: the whole forest fits next to the tiles
+    for (int ci = 0; ci < nCand; ci++) {   // pass 1: the whole forest fits next to WIDE tiles (>= 8 warps per CTA)
         const int *c = kCand[ci];
         if (c[1] == 1 && !single_ok) continue;
+        // a resident forest is not worth 32..128-row tiles (1-4 warps per SM: measured 4x slower per row-tree than
+        // 256-row tiles with the forest cut into chunks -- 256 trees, d = 128: 95 ms vs ~24 ms for 25M rows)
+        if (c[0] < 256) continue;
         if (room_for(c[0], c[1]) >= std::max(need_whole, need_one)) {
             R = c[0];
             S = c[1];
@@ -401,6 +479,16 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
             const int *c = kCand[ci];
             if (c[0] > 256 || (c[1] == 1 && !single_ok)) continue;
             if (room_for(c[0], c[1]) >= std::max<int64_t>(64 * 1024, need_one)) {
+                R = c[0];
+                S = c[1];
+                break;
+            }
+        }
+    if (R == 0)
+        for (int ci = 0; ci < nCand; ci++) {   // pass 3: narrow tiles, whole forest or as many trees as fit
+            const int *c = kCand[ci];
+            if (c[1] == 1 && !single_ok) continue;
+            if (room_for(c[0], c[1]) >= std::max<int64_t>(std::min<int64_t>(need_whole, 48 * 1024), need_one)) {
                 R = c[0];
                 S = c[1];
                 break;
@@ -499,6 +587,45 @@ int ensure_std_generic_tables(ifb_forest *f) {
     return IFB_OK;
 }
 
+}  // namespace ifb
+
+namespace ifb {
+// Forest from the device builder's output without a host copy of the hyperplanes (fit.cu, k == d > 64): the node
+// structure comes from the host tables, the weight rows are gathered on the device.  The builder guarantees the
+// SplitHyperplane invariants (ExtendedUtils.scala:27-34): k distinct ascending indices 0..k-1.
+int create_extended_from_device(int32_t device, int32_t num_trees, const int32_t *node_off, const int32_t *left,
+                                const int32_t *right, const int64_t *num_instances, const double *offset, int32_t k,
+                                const DeviceHyperplanes &dev, int32_t num_samples, int32_t total_num_features,
+                                ifb_forest **out) {
+    *out = nullptr;
+    int rc = validate_shape(num_trees, node_off, left, right, num_instances, /*allow_empty_leaf=*/true);
+    if (rc) return rc;
+    const int64_t total = node_off[num_trees];
+    auto *f = new ifb_forest();
+    f->device = device;
+    f->extended = true;
+    f->num_trees = num_trees;
+    f->num_samples = num_samples;
+    f->total_num_features = total_num_features;
+    f->avg_path_norm = avg_path_length_host(num_samples);
+    f->max_nnz = k;
+    f->max_feature_index = k - 1;
+    f->node_off.assign(node_off, node_off + num_trees + 1);
+    f->left.assign(left, left + total);
+    f->right.assign(right, right + total);
+    f->offset.assign(offset, offset + total);
+    f->num_instances.assign(num_instances, num_instances + total);
+    f->hp_off.assign(total + 1, 0);
+    for (int64_t g = 0; g < total; g++) f->hp_off[g + 1] = f->hp_off[g] + (left[g] != -1 ? k : 0);
+    f->hp_lazy = true;
+    rc = build_extended_tables(f, &dev);
+    if (rc) {
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return IFB_OK;
+}
 }  // namespace ifb
 
 ifb_forest::~ifb_forest() {
@@ -730,7 +857,7 @@ int ifb_forest_get_info(const ifb_forest *f, ifb_forest_info *info) {
     info->max_depth = f->max_depth;
     info->max_nnz = f->max_nnz;
     info->num_nodes = f->node_off.empty() ? 0 : f->node_off.back();
-    info->num_hp_entries = (int64_t)f->hp_idx.size();
+    info->num_hp_entries = f->hp_lazy ? (f->hp_off.empty() ? 0 : f->hp_off.back()) : (int64_t)f->hp_idx.size();
     info->device_bytes = f->device_bytes;
     return IFB_OK;
 }
@@ -749,8 +876,27 @@ int ifb_forest_export(const ifb_forest *f, int32_t *node_off, int32_t *left, int
     if (f->extended) {
         cp(offset, f->offset);
         cp(hp_off, f->hp_off);
-        cp(hp_idx, f->hp_idx);
-        cp(hp_w, f->hp_w);
+        if (f->hp_lazy) {
+            // the weights never left the device: gather them now (pre-order rows, k identity indices each)
+            const int k = f->max_nnz;
+            const int64_t total = f->node_off[f->num_trees], slots = f->ext_internal_slots;
+            std::vector<float> wdev((size_t)slots * k);
+            if (slots > 0 && (hp_w || hp_idx)) {
+                DeviceGuard dg(f->device);
+                if (hp_w) IFB_CUDA(cudaMemcpy(wdev.data(), f->d_ext_w, wdev.size() * 4, cudaMemcpyDeviceToHost));
+                for (int64_t g = 0; g < total; g++) {
+                    const int32_t sl = f->lazy_slot_of_node[(size_t)g];
+                    if (sl < 0) continue;
+                    const int64_t at = f->hp_off[g];
+                    if (hp_w) std::memcpy(hp_w + at, wdev.data() + (size_t)sl * k, (size_t)k * 4);
+                    if (hp_idx)
+                        for (int i = 0; i < k; i++) hp_idx[at + i] = i;
+                }
+            }
+        } else {
+            cp(hp_idx, f->hp_idx);
+            cp(hp_w, f->hp_w);
+        }
     } else {
         cp(feature, f->feature);
         cp(threshold, f->threshold);

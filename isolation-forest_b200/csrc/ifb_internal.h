@@ -101,6 +101,10 @@ struct ifb_forest {
     std::vector<int64_t> num_instances, hp_off;
     std::vector<int32_t> hp_idx;
     std::vector<float> hp_w;
+    // Forests fitted on the device with wide dense hyperplanes (k == d > 64) never bring the weights to the host:
+    // hp_idx / hp_w stay empty, ifb_forest_export gathers them from d_ext_w on demand (forest.cu).
+    bool hp_lazy = false;
+    std::vector<int32_t> lazy_slot_of_node;   // [nodes] pre-order row -> weight slot (row of d_ext_w), -1 at leaves
 
     // ---- standard kernel layout ----
     // host mirrors are kept so that chunking can be re-planned for a different feature count
@@ -177,7 +181,17 @@ namespace ifb {
 
 // forest.cu
 int build_standard_tables(ifb_forest *f);
-int build_extended_tables(ifb_forest *f);
+// Hyperplane weights that already live on the device in the builder's layout (fit.cu): row src_row[g] of `w`
+// (k floats each) belongs to pre-order node g; indices are the identity 0..k-1.
+struct DeviceHyperplanes {
+    const float *w = nullptr;
+    const int64_t *src_row = nullptr;   // host, [nodes], -1 at leaves
+};
+int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev = nullptr);
+int create_extended_from_device(int32_t device, int32_t num_trees, const int32_t *node_off, const int32_t *left,
+                                const int32_t *right, const int64_t *num_instances, const double *offset, int32_t k,
+                                const DeviceHyperplanes &dev, int32_t num_samples, int32_t total_num_features,
+                                ifb_forest **out);
 int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out);   // *out = nullptr: no smem plan, use generic
 int ensure_std_generic_tables(ifb_forest *f);
 int launch_score_standard_generic(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld,

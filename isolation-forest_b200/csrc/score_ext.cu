@@ -159,26 +159,11 @@ struct ScoreExtDenseParams {
     int32_t k;            // real hyperplane width (<= D)
     int32_t fast_ok;      // weights are finite with |w| <= 2^40 and the fast path is not disabled
     double fast_scale;    // dev knob: multiplies the bound (0 = never fall back, huge = always)
-    uint32_t two29;       // 0x20000000, passed at run time so the multiply below stays an IMAD (FMA pipe)
-    uint64_t bias64;      // 0x38000000 << 32
 };
-
-// f32 -> f64 widening of a NORMAL, FINITE, NON-ZERO float with integer ops only (exact: rebias the exponent by
-// 1023-127 = 896, move the 23 mantissa bits to the top of the 52).  Used for a share of the hyperplane terms so
-// that the XU pipe (F2F.F64.F32, 16 lanes/clk/SM -- the measured limiter) shares the conversions with the ALU
-// and FMA pipes.  Callers guarantee the precondition (see `fast` below); everything else takes the F2F path.
-__device__ __forceinline__ double widen_int(float pf, uint32_t two29, uint64_t bias64) {
-    const uint32_t b = __float_as_uint(pf);
-    const uint32_t a = b & 0x7FFFFFFFu;
-    // one IMAD.WIDE: low word = a << 29 (mantissa tail), high word = (a >> 3) + (896 << 20)
-    const uint64_t t = (uint64_t)a * (uint64_t)two29 + bias64;
-    const uint32_t hi = (uint32_t)(t >> 32) | (b & 0x80000000u);
-    return __hiloint2double((int)hi, (int)(uint32_t)t);
-}
 
 // One thread owns one row, held in registers (D floats, zero padded); the trees stream through a 2-slot
 // shared-memory ring, one self-contained blob per tree (forest.cu::build_extended_tables).
-template <int D, int R, int NI>
+template <int D, int R>
 __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseParams p) {
     extern __shared__ __align__(128) unsigned char smem_e[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_e);
@@ -186,8 +171,6 @@ __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseP
     unsigned char *ring = smem_e + 128;
     const int tid = threadIdx.x;
     constexpr int WS = D + 4;
-    const uint32_t two29 = p.two29;
-    const uint64_t bias64 = p.bias64;
     if (tid == 0) {
         mbar_init_e(&bars[0], 1);
         mbar_init_e(&bars[1], 1);
@@ -216,7 +199,9 @@ __global__ void __launch_bounds__(R) score_ext_dense_kernel(const ScoreExtDenseP
 #pragma unroll
         for (int c = 0; c < D; c++) {
             float v = 0.f;
-            if (live && c < p.d)
+            // columns beyond the hyperplane width carry zero weights in the blob; they must read as 0, not as data
+            // (an Inf / NaN there would turn 0 * x into NaN, while the reference never reads those columns)
+            if (live && c < p.k)
                 v = p.layout == IFB_COL_MAJOR ? __ldg(p.X + (int64_t)c * p.ld + row) : __ldg(p.X + row * p.ld + c);
             xr[c] = v;
         }
@@ -323,18 +308,12 @@ int launch_dense(const ifb_forest *f, const ScoreExtDenseParams &p, cudaStream_t
     per_sm = std::max(per_sm, 1);
     const int64_t n_tiles = (p.n_rows + R - 1) / R;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sms * per_sm);
-    static const int ni = getenv("IFB_EXT_NI") ? atoi(getenv("IFB_EXT_NI")) : 1;
     auto go = [&](auto kern) -> int {
         IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, R, smem, stream>>>(p);
         return IFB_OK;
     };
-    int rc;
-    if (ni == 1) rc = go(score_ext_dense_kernel<D, R, 1>);
-    else if (ni == 3) rc = go(score_ext_dense_kernel<D, R, 3>);
-    else if (ni == 4) rc = go(score_ext_dense_kernel<D, R, 4>);
-    else if (ni == 2) rc = go(score_ext_dense_kernel<D, R, 2>);
-    else rc = go(score_ext_dense_kernel<D, R, 1>);
+    int rc = go(score_ext_dense_kernel<D, R>);
     if (rc) return rc;
     IFB_CUDA(cudaGetLastError());
     count_launch();
@@ -646,7 +625,7 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
         q.avg_path = f->avg_path_norm; q.accumulate_only = accumulate_only ? 1 : 0;
         q.scores = scores; q.path_sum = path_sum; q.depth_sum = depth_sum;
         q.k = f->max_nnz; q.fast_ok = (f->ext_w_safe && getenv("IFB_EXT_NOFAST") == nullptr) ? 1 : 0;
-        q.fast_scale = getenv("IFB_EXT_FAST_SCALE") ? atof(getenv("IFB_EXT_FAST_SCALE")) : 1.0; q.two29 = 0x20000000u; q.bias64 = 0x3800000000000000ull;
+        q.fast_scale = getenv("IFB_EXT_FAST_SCALE") ? atof(getenv("IFB_EXT_FAST_SCALE")) : 1.0;
         int rc;
         switch (f->ext_blob_D) {
             case 8: rc = launch_dense<8>(f, q, stream); break;

@@ -389,13 +389,17 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         const float2 *ne = M->ne + gbase + cc * 32;
                         uint32_t Lq[4] = {0, 0, 0, 0}, Aq[4] = {0, 0, 0, 0};   // four short dependency chains per mask
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float2 c = ne[j];                                   // warp-uniform (broadcast) load
-                            const float dlt = fmaf(c.x, scr, __uint_as_float(v[j]));  // S' - offset' * 2^-e_row
-                            const float bound = HOOK ? c.y * p.eb_scale : c.y;
-                            const float tt = fabsf(dlt) - bound;                      // < 0: the visit is ambiguous
-                            Lq[j >> 3] = __funnelshift_l(__float_as_uint(dlt), Lq[j >> 3], 1);   // append the sign bits
-                            Aq[j >> 3] = __funnelshift_l(__float_as_uint(tt), Aq[j >> 3], 1);
+                        for (int j = 0; j < 32; j += 2) {
+                            // {-offset', bound} of two columns in one warp-uniform (broadcast) 16-byte load
+                            const float4 c = reinterpret_cast<const float4 *>(ne)[j >> 1];
+                            const float d0 = fmaf(c.x, scr, __uint_as_float(v[j]));       // S' - offset' * 2^-e_row
+                            const float d1 = fmaf(c.z, scr, __uint_as_float(v[j + 1]));
+                            const float t0 = fabsf(d0) - (HOOK ? c.y * p.eb_scale : c.y); // < 0: the visit is ambiguous
+                            const float t1 = fabsf(d1) - (HOOK ? c.w * p.eb_scale : c.w);
+                            Lq[j >> 3] = __funnelshift_l(__float_as_uint(d0), Lq[j >> 3], 1);   // append the sign bits
+                            Aq[j >> 3] = __funnelshift_l(__float_as_uint(t0), Aq[j >> 3], 1);
+                            Lq[j >> 3] = __funnelshift_l(__float_as_uint(d1), Lq[j >> 3], 1);
+                            Aq[j >> 3] = __funnelshift_l(__float_as_uint(t1), Aq[j >> 3], 1);
                         }
                         // column j of the chunk ends up in bit 31 - j
                         const uint32_t L = (Lq[0] << 24) | (Lq[1] << 16) | (Lq[2] << 8) | Lq[3];

@@ -157,3 +157,28 @@ def test_fit_host_reads_only_the_addressed_extent(nat, oracle):
     wide = np.full((n, d + 3), np.nan, np.float32)
     wide[:, :d] = X
     assert_tables_equal(nat.fit_host(wide[:, :d], prm).export(), ref)   # row-major, ld = d + 3
+
+
+def test_wide_extended_fit_keeps_the_hyperplanes_on_the_device(nat, oracle, monkeypatch):
+    """k == d > 64: the weights are gathered into the scoring tables on the device and only come back to the host on
+    export.  Tables (incl. every weight bit) == oracle == the host-staged build; scoring parity on the same forest."""
+    n_rows, d, T = 6000, 160, 7
+    X = synth_mixture(n_rows, d, 300 + d)
+    ref = oracle.fit_forest(X, T, 256, random_seed=2, ext_level=d - 1)
+    F = fit_gpu(nat, X, T, 256, seed=2, ext=d - 1)
+    got = F.export()
+    assert_tables_equal(got, ref)
+    assert F.info().num_hp_entries == len(ref["hp_w"])
+    monkeypatch.setenv("IFB_FIT_HOST_HP", "1")
+    assert_tables_equal(fit_gpu(nat, X, T, 256, seed=2, ext=d - 1).export(), ref)
+    monkeypatch.delenv("IFB_FIT_HOST_HP")
+    Xd = torch.from_numpy(np.ascontiguousarray(X.T)).cuda().t()
+    s, dd, pp = F.score_device(Xd, want_parts=True)
+    rs, rd, rp = oracle.Forest(ref).score(X, threads=8, want_parts=True)
+    assert np.array_equal(dd.cpu().numpy(), rd) and np.array_equal(pp.cpu().numpy(), rp)
+    assert np.max(np.abs(s.cpu().numpy() - rs) / rs) <= 1e-12
+    for env in ("IFB_EXT_NO_TC", "IFB_EXT_GENERIC"):        # the CUDA-core kernels read the gathered tables too
+        monkeypatch.setenv(env, "1")
+        s2, d2, p2 = F.score_device(Xd, want_parts=True)
+        assert np.array_equal(d2.cpu().numpy(), rd) and np.array_equal(p2.cpu().numpy(), rp)
+        monkeypatch.delenv(env)

@@ -137,9 +137,10 @@ def test_special_values(nat, oracle, dev):
 
 
 def test_extended_dense_special_values_take_the_exact_path(nat, oracle, dev):
-    """The dense extended kernel widens part of the f32 products with integer ops when every lane of a warp has
-    'ordinary' features (finite, non-zero, 2^-60 <= |x| <= 2^60); rows with zeros, denormals, huge values, infs or
-    NaNs must fall back to the F2F path and still match the oracle bit for bit."""
+    """Fully-extended forests decide most visits from a fast filter (tcgen05 accumulators, or the f32 FMA tier of the
+    CUDA-core kernels) that is only valid for 'ordinary' rows (finite, 2^-60 <= |x| <= 2^60); rows with zeros,
+    denormals, huge values, infs or NaNs must take the exact path and still match the oracle bit for bit -- on the
+    tensor-core path and, with IFB_EXT_NO_TC=1, on the dense register kernel."""
     n, d = 8192, 64
     X = synth_mixture(n, d, 77)
     te = oracle.fit_forest(X, 12, 256, random_seed=8, ext_level=d - 1)
@@ -158,6 +159,36 @@ def test_extended_dense_special_values_take_the_exact_path(nat, oracle, dev):
     assert_parity(F.score_device(colmajor_cuda(Xs), want_parts=True), ref)
     # and the all-ordinary matrix (fast path everywhere) as well
     assert_parity(F.score_device(colmajor_cuda(X), want_parts=True), oracle.Forest(te).score(X, threads=8, want_parts=True))
+    import os
+    os.environ["IFB_EXT_NO_TC"] = "1"          # the CUDA-core dense kernel on the same inputs
+    try:
+        assert_parity(F.score_device(colmajor_cuda(Xs), want_parts=True), ref)
+    finally:
+        del os.environ["IFB_EXT_NO_TC"]
+
+
+def test_extended_identity_hyperplanes_narrower_than_the_matrix(nat, oracle, dev):
+    """Hyperplanes over the first k of d > k columns (a hand-built forest): columns the model never reads may hold
+    Inf / NaN without poisoning the dot product (the reference never touches them)."""
+    rng = np.random.default_rng(12)
+    n, d, k, T = 4096, 10, 6, 9
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[::3, 7] = np.inf
+    X[1::3, 8] = np.nan
+    X[2::3, 9] = -np.inf
+    w = rng.standard_normal((T, k)).astype(np.float32)
+    w /= np.linalg.norm(w, axis=1, keepdims=True).astype(np.float32)
+    tables = dict(extended=True, num_trees=T, num_samples=256, total_num_features=d,
+                  node_off=np.arange(0, 3 * T + 1, 3, dtype=np.int32), left=np.tile([1, -1, -1], T).astype(np.int32),
+                  right=np.tile([2, -1, -1], T).astype(np.int32), num_instances=np.tile([-1, 3, 200], T).astype(np.int64),
+                  offset=np.concatenate([[o, 0.0, 0.0] for o in rng.standard_normal(T)]),
+                  hp_off=np.concatenate([[0], np.cumsum(np.tile([k, 0, 0], T))]).astype(np.int64),
+                  hp_idx=np.tile(np.arange(k, dtype=np.int32), T), hp_w=w.reshape(-1))
+    F = nat.NativeForest.from_tables(tables)
+    with np.errstate(all="ignore"):
+        ref = oracle.Forest(tables).score(X, threads=4, want_parts=True)
+    assert_parity(F.score_device(colmajor_cuda(X), want_parts=True), ref)
+    assert_parity(F.score_device(torch.from_numpy(X).cuda(), want_parts=True), ref)
 
 
 def test_extended_wide_kernel_special_values(nat, oracle, dev):
