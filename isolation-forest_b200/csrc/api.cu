@@ -269,35 +269,50 @@ int ifb_score_host(const ifb_forest *f, const float *X, int64_t n_rows, int32_t 
     chunk = std::min<int64_t>(chunk, (n_rows + 3) & ~3ll);
     const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
     const int slots = (int)std::min<int64_t>(kSlots, n_chunks);
-    // streams and stream-ordered scratch of this call; released on every exit path
+    // Streams are cached per (host thread, device): a Spark task thread scores batch after batch, and creating and
+    // destroying three streams per call was visible in small batches (config 1: 1,000 rows).  The stream-ordered
+    // scratch comes from the device's memory pool (release threshold raised in tune_mempool) and is returned on every
+    // exit path.  The streams of a thread live until the process ends.
+    struct StreamSet {
+        cudaStream_t st[kSlots] = {};
+        bool ok = false;
+    };
+    thread_local StreamSet tl_streams[16];
+    StreamSet *cached = (f->device >= 0 && f->device < 16) ? &tl_streams[f->device] : nullptr;
+    StreamSet own;
+    StreamSet *ss = cached ? cached : &own;
+    if (!ss->ok) {
+        for (int i = 0; i < kSlots; i++) IFB_CUDA(cudaStreamCreateWithFlags(&ss->st[i], cudaStreamNonBlocking));
+        ss->ok = true;
+    }
     struct Pipe {
         cudaStream_t st[kSlots] = {};
-        bool live[kSlots] = {};
+        bool owned = false;
+        int slots = 0;
         float *dX[kSlots] = {};
         double *dS[kSlots] = {};
         int32_t *dD[kSlots] = {};
         float *dP[kSlots] = {};
         ~Pipe() {
-            for (int i = 0; i < kSlots; i++) {
-                if (!live[i]) continue;
+            for (int i = 0; i < slots; i++) {
                 if (dX[i]) cudaFreeAsync(dX[i], st[i]);
                 if (dS[i]) cudaFreeAsync(dS[i], st[i]);
                 if (dD[i]) cudaFreeAsync(dD[i], st[i]);
                 if (dP[i]) cudaFreeAsync(dP[i], st[i]);
                 cudaStreamSynchronize(st[i]);
-                cudaStreamDestroy(st[i]);
             }
+            if (owned)
+                for (int i = 0; i < kSlots; i++) cudaStreamDestroy(st[i]);
         }
     } pipe;
+    pipe.owned = cached == nullptr;
+    pipe.slots = slots;
+    for (int i = 0; i < kSlots; i++) pipe.st[i] = ss->st[i];
     cudaStream_t *st = pipe.st;
     float **dX = pipe.dX;
     double **dS = pipe.dS;
     int32_t **dD = pipe.dD;
     float **dP = pipe.dP;
-    for (int i = 0; i < slots; i++) {
-        IFB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-        pipe.live[i] = true;
-    }
     for (int i = 0; i < slots; i++) {
         IFB_CUDA(cudaMallocAsync((void **)&dX[i], (size_t)chunk * d * 4, st[i]));
         IFB_CUDA(cudaMallocAsync((void **)&dS[i], (size_t)chunk * 8, st[i]));

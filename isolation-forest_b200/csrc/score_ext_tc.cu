@@ -23,13 +23,13 @@
 //   ext_tc_prepare_rows   per call: row scaling, fp16 hi/lo split, row norm, row-major f32 copy for the exact path.
 //   score_ext_tc_kernel   persistent, warp-specialised: warp 0 = TMA producer (A = rows, B = hyperplanes, 64-byte
 //                         swizzled K-major tiles), warp 1 = tcgen05.mma issuer (128 x 256 x 16 fp16, f32 accumulators,
-//                         two 256-column TMEM buffers), warps 2-9 = epilogue.  A pair of epilogue warps shares a TMEM lane
-//                         quarter (32 rows); one drains and walks the trees of columns [0,128) of every block, the
-//                         other those of [128,256): tcgen05.ld 32 accumulators at a time, turn every one into two
-//                         bits (left? / ambiguous?) appended to per-lane mask words (no per-column store), park the
-//                         8 mask words in shared memory, walk the half's trees on the masks (4 chains in flight per
-//                         lane), resolve ambiguous visits exactly, and hand the leaf values to the pair's first warp,
-//                         which adds them in tree order (the reference's sequential f32 sum).
+//                         two 256-column TMEM buffers), warps 2-17 = epilogue.  Four epilogue warps share a TMEM lane
+//                         quarter (32 rows).  Drain, split by COLUMNS: each warp tcgen05.ld's two 32-column chunks of
+//                         the block and turns every accumulator into two bits (left? / ambiguous?) appended to
+//                         per-lane mask words (no per-column store); the quad's 16 mask words meet in shared memory.
+//                         Walk, split by TREES: each warp walks a quarter of the block's trees on the masks (up to
+//                         4 chains in flight per lane), resolves ambiguous visits exactly and hands the leaf values
+//                         to the quad's first warp, which adds them in tree order (the reference's sequential f32 sum).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -47,8 +47,6 @@ namespace tc {
 
 constexpr int BM = 128;        // rows per tile (TMEM lanes)
 constexpr int BN = 256;        // hyperplanes (accumulator columns) per block
-constexpr int MAX_TREE_COLS = 160;   // widest tree (internal nodes) the layout accepts
-constexpr int MAX_GROUP_SPAN = 192;  // columns one epilogue warp drains per block, from a 32-aligned base (6 LDTM chunks)
 constexpr int BK = 32;         // K chunk in elements (64 bytes of fp16: one 64B swizzle atom row)
 constexpr int STAGES = 3;
 constexpr int MAX_TREES_PER_BLOCK = 16;
@@ -56,7 +54,7 @@ constexpr int MAX_LEAVES_PER_BLOCK = 512;
 constexpr uint32_t A_BYTES = BM * BK * 2;   //  8 KB
 constexpr uint32_t B_BYTES = BN * BK * 2;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl: 48 KB
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;
 constexpr int META_RING = 4;     // block descriptors in flight: the producer runs ahead of the epilogue by up to 4 blocks
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 
@@ -68,21 +66,19 @@ struct BlockMeta {
     float leafv[MAX_LEAVES_PER_BLOCK];
     uint16_t root[MAX_TREES_PER_BLOCK];
     int32_t n_trees;          // consecutive trees of the ensemble, columns assigned in tree order
-    int32_t n_trees_g0;       // trees [0, n_trees_g0) are drained and walked by the first warp of a pair, the rest by the second
-    int32_t gbase[2];         // first column of each group, rounded down to a multiple of 32
-    int32_t gchunks[2];       // 32-column chunks each group drains (<= 6)
+    int32_t n_cols;           // used columns
     int32_t tree0;
-    int32_t pad;
+    int32_t pad[5];
 };
 static_assert(sizeof(BlockMeta) % 16 == 0, "bulk copies need 16-byte multiples");
 constexpr uint32_t META_BYTES = sizeof(BlockMeta);
 
 // shared-memory carve-up (offsets from a 1024-aligned base)
 constexpr uint32_t OFF_STAGES = 0;
-constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;          // per epilogue warp: lm[8][32], am[8][32]
-constexpr uint32_t OFF_LV = OFF_MASKS + EPI_WARPS * 2048;                  // [2][MAX_TREES_PER_BLOCK][128] leaf values
-constexpr uint32_t OFF_DSX = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;    // [128] depth counts of the second warps
-constexpr uint32_t OFF_META = OFF_DSX + BM * 4;
+constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;          // per lane quarter: lm[8][32], am[8][32]
+constexpr uint32_t OFF_LV = OFF_MASKS + 4 * 2048;                          // [2][MAX_TREES_PER_BLOCK][128] leaf values
+constexpr uint32_t OFF_DSX = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;    // [3][128] depth counts of warps 1..3 of a quad
+constexpr uint32_t OFF_META = OFF_DSX + 3 * BM * 4;
 constexpr uint32_t OFF_BARS = (OFF_META + META_RING * META_BYTES + 15u) & ~15u;
 constexpr int NBARS = 2 * STAGES + 4 + 2 * META_RING;
 constexpr uint32_t OFF_TMEMPTR = OFF_BARS + NBARS * 8;
@@ -352,14 +348,14 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         }
     } else {
         // ===== epilogue warps: TMEM -> registers -> decision masks -> tree walks =====
-        const int ew = warp - 2;                 // 0..7
+        const int ew = warp - 2;                 // 0..15
         const int q = warp & 3;                  // TMEM lane quarter this warp may access (rows q*32 .. q*32+31 of the tile)
-        const int hh = ew >> 2;                  // the tree group of every block this warp drains and walks
-        uint32_t *lm = reinterpret_cast<uint32_t *>(sm + OFF_MASKS + (uint32_t)ew * 2048u);   // [8][32] "left" bits
-        uint32_t *am = lm + 256;                                                             // [8][32] "ambiguous" bits
+        const int gi = ew >> 2;                  // position in the quad of warps that share the quarter
+        uint32_t *lm = reinterpret_cast<uint32_t *>(sm + OFF_MASKS + (uint32_t)q * 2048u);   // [8][32] "left" bits
+        uint32_t *am = lm + 256;                                                            // [8][32] "ambiguous" bits
         float *lvbuf = reinterpret_cast<float *>(sm + OFF_LV);
         int32_t *dsx = reinterpret_cast<int32_t *>(sm + OFF_DSX);
-        const int pair_bar = 1 + q;              // named barrier of the two warps that share this lane quarter
+        const int quad_bar = 1 + q;              // named barrier of the four warps that share this lane quarter
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t row = tile * BM + q * 32 + lane;
@@ -368,8 +364,8 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             const uint32_t flag = live ? (uint32_t)__ldg(p.rflag + row) : 1u;   // dead lanes behave like zero rows
             const uint32_t amb_or = flag == 2u ? 0xFFFFFFFFu : 0u;               // out-of-range row: everything ambiguous
             const uint32_t amb_and = flag == 1u ? 0u : 0xFFFFFFFFu;              // zero row: S' = 0 exactly, never ambiguous
-            float s = (hh == 0 && p.accumulate_only && live) ? p.path_sum[row] : 0.f;
-            int32_t dsum = (hh == 0 && p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
+            float s = (gi == 0 && p.accumulate_only && live) ? p.path_sum[row] : 0.f;
+            int32_t dsum = (gi == 0 && p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
             for (int b = 0; b < NB; b++, it++) {
                 const int buf = (int)(it & 1u);
                 const int mb = (int)(it % META_RING);
@@ -377,55 +373,52 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 mbar_wait(bar_tfull(buf), (it >> 1) & 1u);
                 tc_fence_after();
                 const BlockMeta *M = reinterpret_cast<const BlockMeta *>(sm + OFF_META + (uint32_t)mb * META_BYTES);
-                const int nt = M->n_trees, nt0 = M->n_trees_g0;
-                const int t0 = hh == 0 ? 0 : nt0, t1 = hh == 0 ? nt0 : nt;
-                const int gbase = M->gbase[hh], nchunks = M->gchunks[hh];
-                // ---- drain: 32 accumulators at a time -> two bits each, appended to the mask words ----
-                if (t1 > t0) {   // warp-uniform
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + gbase);
-                    for (int cc = 0; cc < nchunks; cc++) {
-                        uint32_t v[32];
-                        tmem_ld32(taddr + (uint32_t)cc * 32u, v);
-                        const float2 *ne = M->ne + gbase + cc * 32;
-                        uint32_t Lq[4] = {0, 0, 0, 0}, Aq[4] = {0, 0, 0, 0};   // four short dependency chains per mask
+                const int nt = M->n_trees;
+                const int nchunks = (M->n_cols + 31) >> 5;
+                // ---- drain, split by columns: this warp's two 32-column chunks -> two bits per accumulator ----
+                for (int cc = gi * 2; cc < nchunks && cc < gi * 2 + 2; cc++) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cc * 32);
+                    uint32_t v[32];
+                    tmem_ld32(taddr, v);
+                    const float2 *ne = M->ne + cc * 32;
+                    uint32_t Lq[4] = {0, 0, 0, 0}, Aq[4] = {0, 0, 0, 0};   // four short dependency chains per mask
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            // {-offset', bound} of two columns in one warp-uniform (broadcast) 16-byte load
-                            const float4 c = reinterpret_cast<const float4 *>(ne)[j >> 1];
-                            const float d0 = fmaf(c.x, scr, __uint_as_float(v[j]));       // S' - offset' * 2^-e_row
-                            const float d1 = fmaf(c.z, scr, __uint_as_float(v[j + 1]));
-                            const float t0 = fabsf(d0) - (HOOK ? c.y * p.eb_scale : c.y); // < 0: the visit is ambiguous
-                            const float t1 = fabsf(d1) - (HOOK ? c.w * p.eb_scale : c.w);
-                            Lq[j >> 3] = __funnelshift_l(__float_as_uint(d0), Lq[j >> 3], 1);   // append the sign bits
-                            Aq[j >> 3] = __funnelshift_l(__float_as_uint(t0), Aq[j >> 3], 1);
-                            Lq[j >> 3] = __funnelshift_l(__float_as_uint(d1), Lq[j >> 3], 1);
-                            Aq[j >> 3] = __funnelshift_l(__float_as_uint(t1), Aq[j >> 3], 1);
-                        }
-                        // column j of the chunk ends up in bit 31 - j
-                        const uint32_t L = (Lq[0] << 24) | (Lq[1] << 16) | (Lq[2] << 8) | Lq[3];
-                        const uint32_t A = (Aq[0] << 24) | (Aq[1] << 16) | (Aq[2] << 8) | Aq[3];
-                        lm[cc * 32 + lane] = L;
-                        am[cc * 32 + lane] = (A | amb_or) & amb_and;
-                        if (p.probe && tile == 0 && live) {
+                    for (int j = 0; j < 32; j += 2) {
+                        // {-offset', bound} of two columns in one warp-uniform (broadcast) 16-byte load
+                        const float4 c = reinterpret_cast<const float4 *>(ne)[j >> 1];
+                        const float d0 = fmaf(c.x, scr, __uint_as_float(v[j]));       // S' - offset' * 2^-e_row
+                        const float d1 = fmaf(c.z, scr, __uint_as_float(v[j + 1]));
+                        const float t0 = fabsf(d0) - (HOOK ? c.y * p.eb_scale : c.y); // < 0: the visit is ambiguous
+                        const float t1 = fabsf(d1) - (HOOK ? c.w * p.eb_scale : c.w);
+                        Lq[j >> 3] = __funnelshift_l(__float_as_uint(d0), Lq[j >> 3], 1);   // append the sign bits
+                        Aq[j >> 3] = __funnelshift_l(__float_as_uint(t0), Aq[j >> 3], 1);
+                        Lq[j >> 3] = __funnelshift_l(__float_as_uint(d1), Lq[j >> 3], 1);
+                        Aq[j >> 3] = __funnelshift_l(__float_as_uint(t1), Aq[j >> 3], 1);
+                    }
+                    // column j of the chunk ends up in bit 31 - j
+                    const uint32_t L = (Lq[0] << 24) | (Lq[1] << 16) | (Lq[2] << 8) | Lq[3];
+                    const uint32_t A = (Aq[0] << 24) | (Aq[1] << 16) | (Aq[2] << 8) | Aq[3];
+                    lm[cc * 32 + lane] = L;
+                    am[cc * 32 + lane] = (A | amb_or) & amb_and;
+                    if (p.probe && tile == 0 && live) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++)
-                                p.probe[(size_t)row * ((size_t)NB * BN) + (size_t)b * BN + gbase + cc * 32 + j] =
-                                    __uint_as_float(v[j]);
-                        }
+                        for (int j = 0; j < 32; j++)
+                            p.probe[(size_t)row * ((size_t)NB * BN) + (size_t)b * BN + cc * 32 + j] = __uint_as_float(v[j]);
                     }
                 }
-                // the accumulator buffer is free as soon as both halves are in registers / masks
+                // the accumulator buffer is free as soon as every warp's chunks are in its registers / masks
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty(buf));
-                // ---- walk this half's trees on the masks, four chains in flight per lane ----
+                asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");   // the quad's 16 mask words are complete
+                // ---- walk, split by trees: trees gi, gi + 4, gi + 8, ... of the block, up to four chains per lane ----
                 float *lv = lvbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + q * 32 + lane;
-                auto walk_group = [&](auto nch_tag, int tg) {
+                auto walk_group = [&](auto nch_tag) {
                     constexpr int NCH = decltype(nch_tag)::value;
                     uint32_t cur[NCH];
                     uint32_t stuck = 0;   // bit c: chain c waits for an exact decision
 #pragma unroll
-                    for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[tg + c] : 0x8000u;
+                    for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[gi + 4 * c] : 0x8000u;
                     while (true) {
                         // branch-free levels: a chain that sits on a leaf or waits for an exact decision stays put, so
                         // the NCH chains' loads issue back to back (no divergence, no per-level vote)
@@ -434,10 +427,10 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 #pragma unroll
                             for (int c = 0; c < NCH; c++) {
                                 const uint32_t cu = cur[c];
-                                const uint32_t cl = (cu - (uint32_t)gbase) & (BN - 1);   // column relative to the group's base
+                                const uint32_t cl = cu & (BN - 1);
                                 const uint32_t idx = (cl & 224u) | (uint32_t)lane, sh = (~cl) & 31u;
                                 const uint32_t Lw = lm[idx], Aw = am[idx];
-                                const uint32_t rf = M->refs[cu & (BN - 1)];
+                                const uint32_t rf = M->refs[cl];
                                 const uint32_t amb = (Aw >> sh) & 1u, lft = (Lw >> sh) & 1u;
                                 const uint32_t act = ((cu >> 15) ^ 1u) & ((stuck >> c) ^ 1u) & 1u;
                                 const uint32_t adv = act & (amb ^ 1u);
@@ -474,37 +467,26 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < NCH; c++) lv[(tg + c) * BM] = M->leafv[cur[c] & 0x7FFFu];
+                    for (int c = 0; c < NCH; c++) lv[(gi + 4 * c) * BM] = M->leafv[cur[c] & 0x7FFFu];
                 };
-                for (int tg = t0; tg < t1;) {
-                    const int left_trees = t1 - tg;
-                    if (left_trees >= 4) {
-                        walk_group(std::integral_constant<int, 4>{}, tg);
-                        tg += 4;
-                    } else if (left_trees == 3) {
-                        walk_group(std::integral_constant<int, 3>{}, tg);
-                        tg += 3;
-                    } else if (left_trees == 2) {
-                        walk_group(std::integral_constant<int, 2>{}, tg);
-                        tg += 2;
-                    } else {
-                        walk_group(std::integral_constant<int, 1>{}, tg);
-                        tg += 1;
-                    }
-                }
-                // ---- the pair meets; its first warp adds the block's leaf values in tree order ----
-                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-                if (hh == 0) {
+                const int my_trees = nt > gi ? (nt - gi + 3) >> 2 : 0;   // <= MAX_TREES_PER_BLOCK / 4 = 4
+                if (my_trees == 4) walk_group(std::integral_constant<int, 4>{});
+                else if (my_trees == 3) walk_group(std::integral_constant<int, 3>{});
+                else if (my_trees == 2) walk_group(std::integral_constant<int, 2>{});
+                else if (my_trees == 1) walk_group(std::integral_constant<int, 1>{});
+                // ---- the quad meets again; its first warp adds the block's leaf values in tree order ----
+                asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+                if (gi == 0) {
                     for (int t = 0; t < nt; t++) s = s + lv[t * BM];
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_mempty(mb));
             }
-            // depth counts of the pair's second warp travel through shared memory
-            if (hh == 1) dsx[q * 32 + lane] = dsum;
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            if (hh == 0 && live) {
-                dsum += dsx[q * 32 + lane];
+            // depth counts of the quad's other warps travel through shared memory
+            if (gi > 0) dsx[(gi - 1) * BM + q * 32 + lane] = dsum;
+            asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+            if (gi == 0 && live) {
+                dsum += dsx[q * 32 + lane] + dsx[BM + q * 32 + lane] + dsx[2 * BM + q * 32 + lane];
                 if (!p.accumulate_only) {
                     // IF/extended/ExtendedIsolationForestModel.scala:116-119: Float sum / Int, -Float / Float, Math.pow(2, Double)
                     const float e = __fdiv_rn(s, (float)p.total_trees);
@@ -514,7 +496,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 if (p.path_sum) p.path_sum[row] = s;
                 if (p.depth_sum) p.depth_sum[row] = dsum;
             }
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // dsx is free for the next tile
+            asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");   // dsx is free for the next tile
         }
     }
     tc_fence_before();
@@ -755,14 +737,13 @@ int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const 
         const int n = f->node_off[t + 1] - f->node_off[t];
         int m = 0;
         for (int q = 0; q < n; q++) m += child[base + q] >= 0;
-        if (m > MAX_TREE_COLS) return IFB_OK;   // a tree wider than one warp's span: the forest keeps the CUDA-core kernels
+        if (m > BN || n - m > MAX_LEAVES_PER_BLOCK) return IFB_OK;   // a tree wider than one block: CUDA-core kernels
         tm[t] = m;
         tl[t] = n - m;
     }
     std::vector<int32_t> ref_of;
     for (int ta = 0; ta < T;) {
-        // greedily take consecutive trees, then split them into two consecutive groups (one per warp of a pair) whose
-        // column spans, counted from a 32-aligned base, fit MAX_GROUP_SPAN; balance the two spans
+        // consecutive trees, columns in tree order, as many as fit 256 columns / 16 trees / 512 leaves
         int cnt = 0, cols = 0, leaves = 0;
         while (ta + cnt < T && cnt < MAX_TREES_PER_BLOCK && cols + tm[ta + cnt] <= BN &&
                leaves + tl[ta + cnt] <= MAX_LEAVES_PER_BLOCK) {
@@ -770,37 +751,11 @@ int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const 
             leaves += tl[ta + cnt];
             cnt++;
         }
-        int best_s = -1, best_c0 = 0;
-        while (true) {
-            int best_cost = 1 << 30;
-            int c0 = 0;
-            for (int sidx = 0; sidx <= cnt; sidx++) {   // group 0 = trees [ta, ta+sidx)
-                const int span0 = c0, span1 = cols - (c0 / 32) * 32;
-                if (span0 <= MAX_GROUP_SPAN && (sidx == cnt || span1 <= MAX_GROUP_SPAN)) {
-                    const int cost = std::max((span0 + 31) / 32, sidx == cnt ? 0 : (span1 + 31) / 32);
-                    if (cost < best_cost) {
-                        best_cost = cost;
-                        best_s = sidx;
-                        best_c0 = c0;
-                    }
-                }
-                if (sidx < cnt) c0 += tm[ta + sidx];
-            }
-            if (best_s >= 0 || cnt <= 1) break;
-            cnt--;   // no feasible split: drop the last tree and retry
-            cols -= tm[ta + cnt];
-            leaves -= tl[ta + cnt];
-        }
-        if (best_s < 0) return IFB_OK;
         new_block(ta);
         BlockMeta *M = &metas.back();
         const int blk = (int)metas.size() - 1;
         M->n_trees = cnt;
-        M->n_trees_g0 = best_s;
-        M->gbase[0] = 0;
-        M->gchunks[0] = (best_c0 + 31) / 32;
-        M->gbase[1] = (best_c0 / 32) * 32;
-        M->gchunks[1] = best_s == cnt ? 0 : (cols - M->gbase[1] + 31) / 32;
+        M->n_cols = cols;
         int used = 0, n_leaves = 0;
         for (int i = 0; i < cnt; i++) {
             const int t = ta + i;

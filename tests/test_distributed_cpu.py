@@ -100,3 +100,60 @@ def test_gloo_world2_tree_sharding(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def _hybrid_worker(rank, world, port, tmp):
+    """Hybrid rows x trees layout on 4 gloo ranks: 2 row groups x 2 tree shards; the reduce-scatter inside a group is
+    emulated with the group's all-reduce (gloo has no reduce_scatter_tensor) and the slice arithmetic of
+    distributed.score_tree_sharded_rs."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+
+    g.load_package()
+    O = g.load_oracle()
+    from isolation_forest_b200 import distributed as D
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        S = 2
+        group, gidx, G = D.hybrid_groups(world, S)
+        assert (gidx, G) == (rank // S, world // S) and dist.get_world_size(group) == S
+        assert dist.get_rank(group) == rank % S
+        X = synth_mixture(3001, 8, 23)                     # odd row count: slices are padded
+        T, ns = 19, 256
+        full = O.fit_forest(X, T, ns, random_seed=7)
+        ref = O.Forest(full).score(X)
+        g0, g1 = D.row_shard(len(X), gidx, G)              # rows of my row group
+        t0, t1 = D.tree_shard(T, rank % S, S)              # my slice of the ensemble
+        _, _, psum = O.Forest(dict(_slice(full, t0, t1), num_samples=ns)).score(X[g0:g1], want_parts=True)
+        ng = g1 - g0
+        per = (ng + S - 1) // S
+        buf = torch.zeros(per * S)
+        buf[:ng] = torch.from_numpy(psum.copy())
+        dist.all_reduce(buf, group=group)                  # sum over the group's tree shards only
+        r = rank % S
+        lo, hi = min(ng, r * per), min(ng, (r + 1) * per)  # my slice of the group's rows
+        e = buf[lo:hi].numpy() / np.float32(T)
+        sc = np.power(2.0, (-e / O.avg_path_length(ns)).astype(np.float64))
+        assert np.max(np.abs(sc - ref[g0 + lo:g0 + hi]) / ref[g0 + lo:g0 + hi]) < 1e-6
+        covered = torch.zeros(len(X))
+        covered[g0 + lo:g0 + hi] = 1
+        dist.all_reduce(covered)                           # every row is finalised by exactly one rank
+        assert torch.all(covered == 1)
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world4_hybrid_rows_x_trees(tmp_path):
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_hybrid_worker, args=(4, port, str(tmp_path)), nprocs=4, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1", "ok2", "ok3"]
