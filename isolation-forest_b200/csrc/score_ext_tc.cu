@@ -156,6 +156,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// The same load delivered to the same shared-memory offset of every CTA of the cluster named in `mask`; each
+// destination CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, int32_t c0, int32_t c1, uint32_t bar,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, "
+        "%3}], [%4], %5;" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -177,6 +196,12 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the same arrive on the mbarrier at this offset in every CTA of the cluster named in `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
 }
 // K-major operand tile with 64-byte swizzle: rows of 64 bytes, 8-row groups 512 bytes apart (SBO), LBO unused,
 // descriptor version 1 (sm_100), layout type 4 = SWIZZLE_64B   (cute::UMMA::SmemDescriptor bit layout)
@@ -234,7 +259,11 @@ __device__ __forceinline__ bool exact_left(const float *__restrict__ xr, const f
 }
 
 // ---- main kernel ------------------------------------------------------------------------------------------------------
-template <bool HOOK>
+// CL = CTAs per cluster.  The hyperplane (B) tiles are the same for every row tile, so the CTAs of a cluster fetch each
+// B tile from L2 ONCE: CTA r loads rows [r*256/CL, (r+1)*256/CL) of wh / wl and TMA-multicasts them into the same stage
+// of all CL CTAs (the operand feed, not the MMA, bounds this kernel: 48 KB per stage per SM from L2 without sharing).
+// A stage may be refilled once the MMAs of ALL CL CTAs have read it: tcgen05.commit arrives on every CTA's empty barrier.
+template <bool HOOK, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                     const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, const Params p) {
@@ -251,10 +280,12 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     auto bar_mempty = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 4 + META_RING + b); };
     uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(sm + OFF_TMEMPTR);
 
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), 1);
+            mbar_init(bar_empty(s), CL);   // one commit per CTA of the cluster
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(bar_tfull(b), 1);
@@ -273,10 +304,13 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // every CTA's barriers are initialised before a peer signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
-    const int64_t n_tiles = (p.n_rows + BM - 1) / BM;
+    // every CTA of a cluster runs the same number of (tile, block, chunk) iterations: CTAs without a real tile left
+    // process an all-out-of-range one (TMA zero fill, dead lanes) so that the shared B pipeline stays in lockstep
+    const int64_t n_tiles = ((p.n_rows + BM - 1) / BM + gridDim.x - 1) / gridDim.x * gridDim.x;
     const int KC = p.kp / BK;
     const int NB = p.n_blocks;
 
@@ -299,8 +333,18 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         mbar_expect_tx(bar_full(stage), STAGE_BYTES);
                         tma_load_2d(st, &map_xh, kc * BK, (int32_t)(tile * BM), bar_full(stage));
                         tma_load_2d(st + A_BYTES, &map_xl, kc * BK, (int32_t)(tile * BM), bar_full(stage));
-                        tma_load_2d(st + 2 * A_BYTES, &map_wh, kc * BK, b * BN, bar_full(stage));
-                        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_wl, kc * BK, b * BN, bar_full(stage));
+                        if constexpr (CL == 1) {
+                            tma_load_2d(st + 2 * A_BYTES, &map_wh, kc * BK, b * BN, bar_full(stage));
+                            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_wl, kc * BK, b * BN, bar_full(stage));
+                        } else {
+                            // my slice of the block's hyperplanes, delivered to every CTA of the cluster
+                            constexpr int SL = BN / CL;
+                            const uint32_t so = cta_rank * (uint32_t)(SL * BK * 2);
+                            tma_load_2d_mc(st + 2 * A_BYTES + so, &map_wh, kc * BK, b * BN + (int)cta_rank * SL, bar_full(stage),
+                                           kClusterMask);
+                            tma_load_2d_mc(st + 2 * A_BYTES + B_BYTES + so, &map_wl, kc * BK, b * BN + (int)cta_rank * SL,
+                                           bar_full(stage), kClusterMask);
+                        }
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1u;
@@ -336,7 +380,9 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                             umma_f16(d_tmem, a_l, b_h, idesc, 1u);
                             umma_f16(d_tmem, a_h, b_l, idesc, 1u);
                         }
-                        umma_commit(bar_empty(stage));   // the stage may be refilled once these MMAs have read it
+                        // the stage may be refilled once these MMAs -- and the peers' -- have read it
+                        if constexpr (CL == 1) umma_commit(bar_empty(stage));
+                        else umma_commit_mc(bar_empty(stage), kClusterMask);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1u;
@@ -501,6 +547,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it / signal it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -853,16 +900,47 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(a + 2 * b_h + b_f + 2 * b_n);
     if (want_stats) IFB_CUDA(cudaMemsetAsync(stats, 0, 8, stream));
 
+    // CTAs per cluster sharing the hyperplane tiles by TMA multicast (IFB_TC_CLUSTER = 1 | 2 | 4 overrides).  Wide
+    // hyperplanes are operand-feed bound (measured, 1M x 1024, 256 trees: 96.6 / 91.2 / 84.6 ms with 1 / 2 / 4 CTAs
+    // per cluster) and take clusters of four; narrow ones are bound by the epilogue's instruction count (10M x 64,
+    // 200 trees: 66.5 / 66.6 / 74.4 ms -- clusters of four strand a few SMs per GPC) and take clusters of two, which
+    // pack the 148 SMs exactly.
+    const int cl_env = getenv("IFB_TC_CLUSTER") ? atoi(getenv("IFB_TC_CLUSTER")) : (kp >= 256 ? 4 : 2);
+    const int CL = (cl_env == 1 || cl_env == 4) ? cl_env : 2;
     CUtensorMap m_wh, m_wl;
-    int rc = make_tc_tmap(&m_wh, f->d_tc_wh, (int64_t)f->tc_blocks * BN, kp, BN);
+    int rc = make_tc_tmap(&m_wh, f->d_tc_wh, (int64_t)f->tc_blocks * BN, kp, BN / CL);
     if (rc) return rc;
-    rc = make_tc_tmap(&m_wl, f->d_tc_wl, (int64_t)f->tc_blocks * BN, kp, BN);
+    rc = make_tc_tmap(&m_wl, f->d_tc_wl, (int64_t)f->tc_blocks * BN, kp, BN / CL);
     if (rc) return rc;
     const int sms = device_sm_count(f->device);
-    IFB_CUDA(cudaFuncSetAttribute(score_ext_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    IFB_CUDA(cudaFuncSetAttribute(score_ext_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     const size_t prep_smem = (size_t)32 * (kp + 1) * 4;
     IFB_CUDA(cudaFuncSetAttribute(ext_tc_prepare_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    // kernel instantiation for (test hook, cluster size)
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+    const bool hook = eb_scale != 1.0f;
+    KernelFn kern = nullptr;
+    if (CL == 1) kern = hook ? score_ext_tc_kernel<true, 1> : score_ext_tc_kernel<false, 1>;
+    else if (CL == 2) kern = hook ? score_ext_tc_kernel<true, 2> : score_ext_tc_kernel<false, 2>;
+    else kern = hook ? score_ext_tc_kernel<true, 4> : score_ext_tc_kernel<false, 4>;
+    IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    // how many clusters are co-resident (one CTA per SM; clusters never span GPCs)
+    int max_clusters = sms / CL;
+    if (CL > 1) {
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3((unsigned)(sms / CL * CL));
+        qc.blockDim = dim3(THREADS);
+        qc.dynamicSmemBytes = SMEM_BYTES;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = (unsigned)CL;
+        qa[0].val.clusterDim.y = 1;
+        qa[0].val.clusterDim.z = 1;
+        qc.attrs = qa;
+        qc.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, kern, &qc) == cudaSuccess && nc > 0) max_clusters = std::min(max_clusters, nc);
+        else cudaGetLastError();
+    }
 
     for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
         const int64_t rows = std::min<int64_t>(chunk, n_rows - r0);
@@ -899,9 +977,21 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
         p.probe = (probe_out && r0 == 0) ? probe_out : nullptr;
         p.stats = want_stats ? stats : nullptr;
         const int64_t n_tiles = (rows + BM - 1) / BM;
-        const int grid = (int)std::min<int64_t>(n_tiles, sms);
-        if (eb_scale != 1.0f) score_ext_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(m_xh, m_xl, m_wh, m_wl, p);
-        else score_ext_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(m_xh, m_xl, m_wh, m_wl, p);
+        const int64_t want_clusters = (n_tiles + CL - 1) / CL;
+        const int grid = (int)std::min<int64_t>(want_clusters, max_clusters) * CL;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = CL > 1 ? 1 : 0;
+        IFB_CUDA(cudaLaunchKernelEx(&cfg, kern, m_xh, m_xl, m_wh, m_wl, p));
         IFB_CUDA(cudaGetLastError());
         count_launch();
     }
