@@ -198,6 +198,7 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
     std::vector<double> off(total, 0.0);
     std::vector<float> leaf(total, 0.f);
     std::vector<int32_t> child(total, -1), hp(total, -1), len(total, 0);
+    std::vector<uint8_t> depthv(total, 0);   // BFS-order depth of every node (leaf depth = internal nodes on its path)
     std::vector<int64_t> tree_node(f->node_off.begin(), f->node_off.end());
     int64_t internal = 0;
     for (int64_t g = 0; g < total; g++) internal += (f->left[g] != -1);
@@ -218,6 +219,7 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
         for (int32_t q = 0; q < n; q++) {
             const int32_t id = order[q];
             const int64_t g = base + q, src = base + id;
+            depthv[g] = (uint8_t)std::min(dep[q], 255);
             if (f->left[src] == -1) {
                 volatile float v = (float)dep[q] + avg_path_length_host(f->num_instances[src]);
                 leaf[g] = v;
@@ -412,7 +414,7 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
     }
     // tensor-core layout (fully-extended forests; a forest that does not qualify simply keeps tc_ok = false)
     if (f->ext_dense_identity && getenv("IFB_EXT_NO_TC") == nullptr) {
-        rc = build_ext_tc_tables(f, child, hp, leaf, off);
+        rc = build_ext_tc_tables(f, child, hp, leaf, off, depthv);
         if (rc) return rc;
     }
     return IFB_OK;

@@ -223,7 +223,7 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
                           bool accumulate_only, cudaStream_t stream);
 // score_ext_tc.cu: tensor-core path of fully-extended forests; returns -1 when the forest / call does not qualify
 int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const std::vector<int32_t> &hp,
-                        const std::vector<float> &leaf, const std::vector<double> &off);
+                        const std::vector<float> &leaf, const std::vector<double> &off, const std::vector<uint8_t> &depth);
 int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
                              double *scores, int32_t *depth_sum, float *path_sum, bool accumulate_only,
                              cudaStream_t stream, float *probe_out = nullptr);

@@ -50,20 +50,25 @@ constexpr int BN = 256;        // hyperplanes (accumulator columns) per block
 constexpr int BK = 32;         // K chunk in elements (64 bytes of fp16: one 64B swizzle atom row)
 constexpr int STAGES = 3;
 constexpr int MAX_TREES_PER_BLOCK = 16;
-constexpr int MAX_LEAVES_PER_BLOCK = 512;
+constexpr int MAX_LEAVES_PER_BLOCK = 256;   // node ids stay below 512: bit 8 alone tells a leaf from an internal node
 constexpr uint32_t A_BYTES = BM * BK * 2;   //  8 KB
 constexpr uint32_t B_BYTES = BN * BK * 2;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl: 48 KB
 constexpr int EPI_WARPS = 16;
-constexpr int META_RING = 4;     // block descriptors in flight: the producer runs ahead of the epilogue by up to 4 blocks
+constexpr int META_RING = 3;     // block descriptors in flight: the producer runs ahead of the epilogue by up to 3 blocks
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 
+// Node ids inside a block: [0, 256) = internal nodes (= accumulator columns), 256 + i = leaf i of the block.
+constexpr uint32_t LEAF0 = BN;
+constexpr int MAX_NODES_PER_BLOCK = BN + MAX_LEAVES_PER_BLOCK;
 struct BlockMeta {
     float2 ne[BN];            // per column (= internal node): {-offset', bound}: offset' = offset * 2^-s_node rounded to
                               // f32; the visit is certain iff |S' - offset' * 2^-e_row| >= bound  (bound > c_k ||w'||)
-    uint32_t refs[BN];        // left | right << 16;  ref = column in the block, or 0x8000 | leaf index
+    uint2 next[MAX_NODES_PER_BLOCK];   // {left, right} node ids; a leaf points at itself, so a walk is a fixed number of
+                                       // branch-free steps
     int32_t slot[BN];         // weight slot (row of d_ext_w) for the exact path; -1: padding column
-    float leafv[MAX_LEAVES_PER_BLOCK];
+    float leafv[MAX_LEAVES_PER_BLOCK];   // (float)depth + c(numInstances)
+    uint8_t leafd[MAX_LEAVES_PER_BLOCK]; // depth of the leaf = internal nodes visited on the way (depth_sum output)
     uint16_t root[MAX_TREES_PER_BLOCK];
     int32_t n_trees;          // consecutive trees of the ensemble, columns assigned in tree order
     int32_t n_cols;           // used columns
@@ -75,7 +80,7 @@ constexpr uint32_t META_BYTES = sizeof(BlockMeta);
 
 // shared-memory carve-up (offsets from a 1024-aligned base)
 constexpr uint32_t OFF_STAGES = 0;
-constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;          // per lane quarter: lm[8][32], am[8][32]
+constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;          // per lane quarter: {left, ambiguous} words [8][32]
 constexpr uint32_t OFF_LV = OFF_MASKS + 4 * 2048;                          // [2][MAX_TREES_PER_BLOCK][128] leaf values
 constexpr uint32_t OFF_DSX = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;    // [3][128] depth counts of warps 1..3 of a quad
 constexpr uint32_t OFF_META = OFF_DSX + 3 * BM * 4;
@@ -397,8 +402,8 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         const int ew = warp - 2;                 // 0..15
         const int q = warp & 3;                  // TMEM lane quarter this warp may access (rows q*32 .. q*32+31 of the tile)
         const int gi = ew >> 2;                  // position in the quad of warps that share the quarter
-        uint32_t *lm = reinterpret_cast<uint32_t *>(sm + OFF_MASKS + (uint32_t)q * 2048u);   // [8][32] "left" bits
-        uint32_t *am = lm + 256;                                                            // [8][32] "ambiguous" bits
+        // [8 chunks][32 lanes] {"left" bits, "ambiguous" bits}: column j of a chunk sits in bit 31 - j of both words
+        uint2 *mq = reinterpret_cast<uint2 *>(sm + OFF_MASKS + (uint32_t)q * 2048u);
         float *lvbuf = reinterpret_cast<float *>(sm + OFF_LV);
         int32_t *dsx = reinterpret_cast<int32_t *>(sm + OFF_DSX);
         const int quad_bar = 1 + q;              // named barrier of the four warps that share this lane quarter
@@ -444,8 +449,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                     // column j of the chunk ends up in bit 31 - j
                     const uint32_t L = (Lq[0] << 24) | (Lq[1] << 16) | (Lq[2] << 8) | Lq[3];
                     const uint32_t A = (Aq[0] << 24) | (Aq[1] << 16) | (Aq[2] << 8) | Aq[3];
-                    lm[cc * 32 + lane] = L;
-                    am[cc * 32 + lane] = (A | amb_or) & amb_and;
+                    mq[cc * 32 + lane] = make_uint2(L, (A | amb_or) & amb_and);
                     if (p.probe && tile == 0 && live) {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
@@ -461,59 +465,82 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 float *lv = lvbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + q * 32 + lane;
                 auto walk_group = [&](auto nch_tag) {
                     constexpr int NCH = decltype(nch_tag)::value;
-                    uint32_t cur[NCH];
-                    uint32_t stuck = 0;   // bit c: chain c waits for an exact decision
+                    uint32_t cur[NCH], amb[NCH];
 #pragma unroll
-                    for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[gi + 4 * c] : 0x8000u;
-                    while (true) {
-                        // branch-free levels: a chain that sits on a leaf or waits for an exact decision stays put, so
-                        // the NCH chains' loads issue back to back (no divergence, no per-level vote)
+                    for (int c = 0; c < NCH; c++) {
+                        cur[c] = live ? (uint32_t)M->root[gi + 4 * c] : LEAF0;
+                        amb[c] = 0;
+                    }
+                    // fast path: branch-free levels that ignore ambiguity and only remember (bit 31 of amb) whether an
+                    // ambiguous INTERNAL node was visited; leaves point at themselves.  13 instructions per level.
 #pragma unroll 1
-                        for (int lvl = 0; lvl < p.max_depth; lvl++) {
+                    for (int lvl = 0; lvl < p.max_depth; lvl++) {
 #pragma unroll
-                            for (int c = 0; c < NCH; c++) {
-                                const uint32_t cu = cur[c];
-                                const uint32_t cl = cu & (BN - 1);
-                                const uint32_t idx = (cl & 224u) | (uint32_t)lane, sh = (~cl) & 31u;
-                                const uint32_t Lw = lm[idx], Aw = am[idx];
-                                const uint32_t rf = M->refs[cl];
-                                const uint32_t amb = (Aw >> sh) & 1u, lft = (Lw >> sh) & 1u;
-                                const uint32_t act = ((cu >> 15) ^ 1u) & ((stuck >> c) ^ 1u) & 1u;
-                                const uint32_t adv = act & (amb ^ 1u);
-                                cur[c] = adv ? (lft ? (rf & 0xFFFFu) : (rf >> 16)) : cu;
-                                dsum += (int32_t)adv;
-                                stuck |= (act & amb) << c;
-                            }
+                        for (int c = 0; c < NCH; c++) {
+                            const uint32_t cu = cur[c];
+                            const uint32_t j = cu & 31u;
+                            const uint2 m = mq[(cu & 0xE0u) + (uint32_t)lane];
+                            const uint2 nx = M->next[cu];
+                            amb[c] |= (m.y << j) & ~(cu << 23);          // cu >= 256 (a leaf) clears bit 31
+                            cur[c] = ((int32_t)(m.x << j) < 0) ? nx.x : nx.y;
                         }
-                        uint32_t sm_mask = __ballot_sync(0xffffffffu, stuck != 0);
-                        if (!sm_mask) break;
-                        // exact decisions, one stuck (lane, chain) at a time, the whole warp cooperating
-                        while (sm_mask) {
-                            const int Ls = __ffs(sm_mask) - 1;
-                            sm_mask &= sm_mask - 1;
-                            const uint32_t stL = __shfl_sync(0xffffffffu, stuck, Ls);
-                            const int64_t rowL = __shfl_sync(0xffffffffu, row, Ls);
+                    }
+                    uint32_t any_amb = 0;
 #pragma unroll
-                            for (int c = 0; c < NCH; c++) {
-                                if ((stL >> c) & 1u) {   // warp-uniform
-                                    const uint32_t col = __shfl_sync(0xffffffffu, cur[c], Ls);
-                                    const uint32_t rf = M->refs[col];
-                                    const int32_t slot = M->slot[col];
-                                    const double off = __ldg(p.col_off + (size_t)b * BN + col);
-                                    const bool left = exact_left(p.xr + (size_t)rowL * p.kp, p.w + (size_t)slot * p.k, p.k, off,
-                                                                 __ldg(p.wabs + slot), lane);
-                                    if (lane == Ls) {
-                                        cur[c] = left ? (rf & 0xFFFFu) : (rf >> 16);
-                                        dsum++;
-                                        stuck &= ~(1u << c);
+                    for (int c = 0; c < NCH; c++) any_amb |= amb[c];
+                    if (__any_sync(0xffffffffu, (int32_t)any_amb < 0)) {
+                        // careful path (rare at d <= 64, ~1/3 of the groups at d = 1024 where the epilogue is hidden behind
+                        // the MMA): walk again from the roots, stop at ambiguous nodes and decide them exactly, one stuck
+                        // (lane, chain) at a time, the whole warp cooperating
+                        uint32_t stuck = 0;
+#pragma unroll
+                        for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[gi + 4 * c] : LEAF0;
+                        while (true) {
+#pragma unroll 1
+                            for (int lvl = 0; lvl < p.max_depth; lvl++) {
+#pragma unroll
+                                for (int c = 0; c < NCH; c++) {
+                                    const uint32_t cu = cur[c];
+                                    const uint32_t j = cu & 31u;
+                                    const uint2 m = mq[(cu & 0xE0u) + (uint32_t)lane];
+                                    const uint2 nx = M->next[cu];
+                                    const uint32_t a = (((m.y << j) & ~(cu << 23)) >> 31) | ((stuck >> c) & 1u);
+                                    stuck |= a << c;
+                                    cur[c] = a ? cu : (((int32_t)(m.x << j) < 0) ? nx.x : nx.y);
+                                }
+                            }
+                            uint32_t sm_mask = __ballot_sync(0xffffffffu, stuck != 0);
+                            if (!sm_mask) break;
+                            while (sm_mask) {
+                                const int Ls = __ffs(sm_mask) - 1;
+                                sm_mask &= sm_mask - 1;
+                                const uint32_t stL = __shfl_sync(0xffffffffu, stuck, Ls);
+                                const int64_t rowL = __shfl_sync(0xffffffffu, row, Ls);
+#pragma unroll
+                                for (int c = 0; c < NCH; c++) {
+                                    if ((stL >> c) & 1u) {   // warp-uniform
+                                        const uint32_t col = __shfl_sync(0xffffffffu, cur[c], Ls);
+                                        const uint2 nx = M->next[col];
+                                        const int32_t slot = M->slot[col];
+                                        const double off = __ldg(p.col_off + (size_t)b * BN + col);
+                                        const bool left = exact_left(p.xr + (size_t)rowL * p.kp, p.w + (size_t)slot * p.k, p.k,
+                                                                     off, __ldg(p.wabs + slot), lane);
+                                        if (lane == Ls) {
+                                            cur[c] = left ? nx.x : nx.y;
+                                            stuck &= ~(1u << c);
+                                        }
+                                        if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                                     }
-                                    if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                                 }
                             }
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < NCH; c++) lv[(gi + 4 * c) * BM] = M->leafv[cur[c] & 0x7FFFu];
+                    for (int c = 0; c < NCH; c++) {
+                        const uint32_t lf = cur[c] - LEAF0;
+                        lv[(gi + 4 * c) * BM] = M->leafv[lf];
+                        dsum += (int32_t)M->leafd[lf];
+                    }
                 };
                 const int my_trees = nt > gi ? (nt - gi + 3) >> 2 : 0;   // <= MAX_TREES_PER_BLOCK / 4 = 4
                 if (my_trees == 4) walk_group(std::integral_constant<int, 4>{});
@@ -754,11 +781,11 @@ double tc_bound_constant(int k, int kp) {
 }  // namespace
 
 int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const std::vector<int32_t> &hp,
-                        const std::vector<float> &leaf, const std::vector<double> &off) {
+                        const std::vector<float> &leaf, const std::vector<double> &off, const std::vector<uint8_t> &depth) {
     using namespace tc;
     const int T = f->num_trees;
     const int k = f->max_nnz;
-    if (T == 0 || k < 1 || k > 16384 || !f->ext_w_safe) return IFB_OK;
+    if (T == 0 || k < 1 || k > 16384 || !f->ext_w_safe || f->max_depth > 255) return IFB_OK;
     const int kp = (k + BK - 1) / BK * BK;
     // ---- pack whole trees into 128-column halves of 256-column blocks, in tree order ----
     std::vector<BlockMeta> metas;
@@ -770,9 +797,9 @@ int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const 
         std::memset(&m, 0, sizeof m);
         for (int i = 0; i < BN; i++) {
             m.ne[i] = make_float2(0.f, 0.f);
-            m.refs[i] = 0x80008000u;
             m.slot[i] = -1;
         }
+        for (int i = 0; i < MAX_NODES_PER_BLOCK; i++) m.next[i] = make_uint2((uint32_t)i, (uint32_t)i);
         m.tree0 = tree0;
         col_slot.resize(metas.size() * BN, -1);
         col_off.resize(metas.size() * BN, 0.0);
@@ -812,18 +839,19 @@ int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const 
             int ci = 0, li = 0;
             for (int q = 0; q < n; q++) {
                 if (child[base + q] >= 0) ref_of[q] = used + ci++;
-                else ref_of[q] = 0x8000 | (n_leaves + li++);
+                else ref_of[q] = (int)LEAF0 + n_leaves + li++;
             }
             for (int q = 0; q < n; q++) {
                 const int64_t g = base + q;
                 if (child[g] >= 0) {
                     const int col = ref_of[q];
-                    M->refs[col] = (uint32_t)ref_of[child[g]] | ((uint32_t)ref_of[child[g] + 1] << 16);
+                    M->next[col] = make_uint2((uint32_t)ref_of[child[g]], (uint32_t)ref_of[child[g] + 1]);
                     M->slot[col] = hp[g];
                     col_slot[(size_t)blk * BN + col] = hp[g];
                     col_off[(size_t)blk * BN + col] = off[g];
                 } else {
-                    M->leafv[ref_of[q] & 0x7FFF] = leaf[g];
+                    M->leafv[ref_of[q] - (int)LEAF0] = leaf[g];
+                    M->leafd[ref_of[q] - (int)LEAF0] = depth[g];
                 }
             }
             M->root[i] = (uint16_t)ref_of[0];
