@@ -54,7 +54,12 @@ constexpr int MAX_LEAVES_PER_BLOCK = 256;   // node ids stay below 512: bit 8 al
 constexpr uint32_t A_BYTES = BM * BK * 2;   //  8 KB
 constexpr uint32_t B_BYTES = BN * BK * 2;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl: 48 KB
-constexpr int EPI_WARPS = 16;
+#ifndef IFB_TC_EPI_WARPS
+#define IFB_TC_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = IFB_TC_EPI_WARPS;   // 8 or 16
+constexpr int QW = EPI_WARPS / 4;             // epilogue warps per TMEM lane quarter
+static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "two or four epilogue warps per lane quarter");
 constexpr int META_RING = 3;     // block descriptors in flight: the producer runs ahead of the epilogue by up to 3 blocks
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 
@@ -82,7 +87,7 @@ constexpr uint32_t META_BYTES = sizeof(BlockMeta);
 constexpr uint32_t OFF_STAGES = 0;
 constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;          // per lane quarter: {left, ambiguous} words [8][32]
 constexpr uint32_t OFF_LV = OFF_MASKS + 4 * 2048;                          // [2][MAX_TREES_PER_BLOCK][128] leaf values
-constexpr uint32_t OFF_DSX = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;    // [3][128] depth counts of warps 1..3 of a quad
+constexpr uint32_t OFF_DSX = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;    // [3][128] depth counts of warps 1.. of a quarter
 constexpr uint32_t OFF_META = OFF_DSX + 3 * BM * 4;
 constexpr uint32_t OFF_BARS = (OFF_META + META_RING * META_BYTES + 15u) & ~15u;
 constexpr int NBARS = 2 * STAGES + 4 + 2 * META_RING;
@@ -427,7 +432,8 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 const int nt = M->n_trees;
                 const int nchunks = (M->n_cols + 31) >> 5;
                 // ---- drain, split by columns: this warp's two 32-column chunks -> two bits per accumulator ----
-                for (int cc = gi * 2; cc < nchunks && cc < gi * 2 + 2; cc++) {
+                constexpr int CPW = 8 / QW;   // chunks per warp
+                for (int cc = gi * CPW; cc < nchunks && cc < gi * CPW + CPW; cc++) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cc * 32);
                     uint32_t v[32];
                     tmem_ld32(taddr, v);
@@ -460,15 +466,15 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty(buf));
-                asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");   // the quad's 16 mask words are complete
+                asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * QW) : "memory");   // the quad's 16 mask words are complete
                 // ---- walk, split by trees: trees gi, gi + 4, gi + 8, ... of the block, up to four chains per lane ----
                 float *lv = lvbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + q * 32 + lane;
-                auto walk_group = [&](auto nch_tag) {
+                auto walk_group = [&](auto nch_tag, int t0) {   // trees t0 + gi + QW * c, c < NCH
                     constexpr int NCH = decltype(nch_tag)::value;
                     uint32_t cur[NCH], amb[NCH];
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
-                        cur[c] = live ? (uint32_t)M->root[gi + 4 * c] : LEAF0;
+                        cur[c] = live ? (uint32_t)M->root[t0 + gi + QW * c] : LEAF0;
                         amb[c] = 0;
                     }
                     // fast path: branch-free levels that ignore ambiguity and only remember (bit 31 of amb) whether an
@@ -494,7 +500,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         // (lane, chain) at a time, the whole warp cooperating
                         uint32_t stuck = 0;
 #pragma unroll
-                        for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[gi + 4 * c] : LEAF0;
+                        for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[t0 + gi + QW * c] : LEAF0;
                         while (true) {
 #pragma unroll 1
                             for (int lvl = 0; lvl < p.max_depth; lvl++) {
@@ -538,17 +544,30 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
                         const uint32_t lf = cur[c] - LEAF0;
-                        lv[(gi + 4 * c) * BM] = M->leafv[lf];
+                        lv[(t0 + gi + QW * c) * BM] = M->leafv[lf];
                         dsum += (int32_t)M->leafd[lf];
                     }
                 };
-                const int my_trees = nt > gi ? (nt - gi + 3) >> 2 : 0;   // <= MAX_TREES_PER_BLOCK / 4 = 4
-                if (my_trees == 4) walk_group(std::integral_constant<int, 4>{});
-                else if (my_trees == 3) walk_group(std::integral_constant<int, 3>{});
-                else if (my_trees == 2) walk_group(std::integral_constant<int, 2>{});
-                else if (my_trees == 1) walk_group(std::integral_constant<int, 1>{});
+                const int my_trees = nt > gi ? (nt - gi + QW - 1) / QW : 0;   // <= MAX_TREES_PER_BLOCK / QW
+                for (int done = 0; done < my_trees;) {
+                    const int left_trees = my_trees - done;
+                    const int t0 = done * QW;
+                    if (left_trees >= 4) {
+                        walk_group(std::integral_constant<int, 4>{}, t0);
+                        done += 4;
+                    } else if (left_trees == 3) {
+                        walk_group(std::integral_constant<int, 3>{}, t0);
+                        done += 3;
+                    } else if (left_trees == 2) {
+                        walk_group(std::integral_constant<int, 2>{}, t0);
+                        done += 2;
+                    } else {
+                        walk_group(std::integral_constant<int, 1>{}, t0);
+                        done += 1;
+                    }
+                }
                 // ---- the quad meets again; its first warp adds the block's leaf values in tree order ----
-                asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * QW) : "memory");
                 if (gi == 0) {
                     for (int t = 0; t < nt; t++) s = s + lv[t * BM];
                 }
@@ -557,9 +576,10 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             }
             // depth counts of the quad's other warps travel through shared memory
             if (gi > 0) dsx[(gi - 1) * BM + q * 32 + lane] = dsum;
-            asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * QW) : "memory");
             if (gi == 0 && live) {
-                dsum += dsx[q * 32 + lane] + dsx[BM + q * 32 + lane] + dsx[2 * BM + q * 32 + lane];
+#pragma unroll
+                for (int w = 0; w < QW - 1; w++) dsum += dsx[w * BM + q * 32 + lane];
                 if (!p.accumulate_only) {
                     // IF/extended/ExtendedIsolationForestModel.scala:116-119: Float sum / Int, -Float / Float, Math.pow(2, Double)
                     const float e = __fdiv_rn(s, (float)p.total_trees);
@@ -569,7 +589,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 if (p.path_sum) p.path_sum[row] = s;
                 if (p.depth_sum) p.depth_sum[row] = dsum;
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");   // dsx is free for the next tile
+            asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * QW) : "memory");   // dsx is free for the next tile
         }
     }
     tc_fence_before();
