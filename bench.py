@@ -331,6 +331,27 @@ def run_native(args, wl_name, wl):
                "d2h_bytes_per_step": n * 8, "steps": esteps,
                "path": "ifb_score_host: pinned host col-major f32 -> 3-stream chunked H2D/score/D2H -> host f64"}
         e2e["matches_device_path"] = bool(np.array_equal(hs.array, scores.cpu().numpy()))
+        # what bounds e2e: the bare pinned-host -> device copy rate of this rank while every rank copies at once
+        # (min / max over ranks; a drop from N = 1 names the shared host-side path -- root complex / host memory -- not the GPU)
+        hview = torch.from_numpy(hx.array)
+        dbuf = torch.empty_like(X.t())
+        dbuf.copy_(hview, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            dbuf.copy_(hview, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        gbs = 3 * n * d * 4 / (c0.elapsed_time(c1) / 1e3) / 1e9
+        lo = torch.tensor([gbs], dtype=torch.float64, device=dev)
+        hi = lo.clone()
+        if world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        e2e["h2d_copy_gbs_per_rank"] = {"min": float(lo.item()), "max": float(hi.item()),
+                                        "note": "bare cudaMemcpyAsync of the same pinned matrix, all ranks concurrently"}
+        del dbuf, hview
         hx.free(); hs.free()
 
     # ---- parity of what was just timed, against the CPU oracle on the same rows and the same forest (rank 0) ----
