@@ -805,7 +805,9 @@ int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const 
     using namespace tc;
     const int T = f->num_trees;
     const int k = f->max_nnz;
-    if (T == 0 || k < 1 || k > 16384 || !f->ext_w_safe || f->max_depth > 255) return IFB_OK;
+    // k <= 1536: ext_tc_prepare_rows stages 32 rows x (k_pad + 1) floats in shared memory (197 KB at the limit); wider
+    // hyperplanes keep the CUDA-core wide kernel
+    if (T == 0 || k < 1 || k > 1536 || !f->ext_w_safe || f->max_depth > 255) return IFB_OK;
     const int kp = (k + BK - 1) / BK * BK;
     // ---- pack whole trees into 128-column halves of 256-column blocks, in tree order ----
     std::vector<BlockMeta> metas;

@@ -161,3 +161,18 @@ def test_tc_partial_sums_accumulate_across_forest_shards(nat, oracle, dev):
     assert np.array_equal(ps.cpu().numpy(), ref[2])      # same sequential order: shard 0's sum carried into shard 1
     sc = nat.finalize_scores_device(ps, T, 256).cpu().numpy()
     assert np.max(np.abs(sc - ref[0]) / ref[0]) <= 1e-12
+
+
+def test_hyperplanes_wider_than_the_staging_limit_use_the_cuda_core_kernels(nat, oracle, dev):
+    """k > 1536 does not get a tensor-core layout (the row-preparation tile would not fit shared memory); the wide
+    CUDA-core kernel scores it, same parity bar."""
+    n, d, T = 700, 2000, 3
+    X = synth_mixture(n, d, 6000 + d)
+    t = oracle.fit_forest(X, T, 256, random_seed=4, ext_level=d - 1)
+    F = nat.NativeForest.from_tables(t)
+    assert F.ext_tc_info() == (0, 0)
+    ref = oracle.Forest(t).score(X, threads=8, want_parts=True)
+    assert_parity(F.score_device(colmajor_cuda(X), want_parts=True), ref)
+    Fg = nat.fit_device(colmajor_cuda(X), nat.FitParams(T, 256, d, 0, 4, 1, d - 1, 0, 0))    # device-resident hyperplanes
+    assert Fg.ext_tc_info() == (0, 0)
+    assert_parity(Fg.score_device(colmajor_cuda(X), want_parts=True), oracle.Forest(Fg.export()).score(X, threads=8, want_parts=True))
