@@ -69,6 +69,8 @@ constexpr int MAX_NODES_PER_BLOCK = BN + MAX_LEAVES_PER_BLOCK;
 struct BlockMeta {
     float2 ne[BN];            // per column (= internal node): {-offset', bound}: offset' = offset * 2^-s_node rounded to
                               // f32; the visit is certain iff |S' - offset' * 2^-e_row| >= bound  (bound > c_k ||w'||)
+    float nthr[BN];           // -offset' again, densely packed for the drain's fast path (+inf at padding columns)
+    float emax[BN / 32];      // largest bound of each 32-column chunk
     uint2 next[MAX_NODES_PER_BLOCK];   // {left, right} node ids; a leaf points at itself, so a walk is a fixed number of
                                        // branch-free steps
     int32_t slot[BN];         // weight slot (row of d_ext_w) for the exact path; -1: padding column
@@ -235,6 +237,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// min(|a|, |b|, |c|) in one instruction (FMNMX3 with absolute-value modifiers)
+__device__ __forceinline__ float fmin3_abs(float a, float b, float c) {
+    float r;
+    asm("min.abs.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 
 // ---- the exact path: one hyperplane decision for one row, evaluated by the whole warp -------------------------------
@@ -437,24 +446,42 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cc * 32);
                     uint32_t v[32];
                     tmem_ld32(taddr, v);
-                    const float2 *ne = M->ne + cc * 32;
-                    uint32_t Lq[4] = {0, 0, 0, 0}, Aq[4] = {0, 0, 0, 0};   // four short dependency chains per mask
+                    // Fast path (2.75 instructions per column): the "left" bit of every accumulator, and ONE chunk-wide
+                    // test for ambiguity -- the smallest |dlt| of the 32 columns against the largest bound of the chunk.
+                    // Only chunks that fail it (rare at d <= 64) compute the per-column "ambiguous" bits.
+                    const float4 *nt4 = reinterpret_cast<const float4 *>(M->nthr + cc * 32);
+                    uint32_t Lq[4] = {0, 0, 0, 0};   // four short dependency chains
+                    float mn = INFINITY;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        // {-offset', bound} of two columns in one warp-uniform (broadcast) 16-byte load
-                        const float4 c = reinterpret_cast<const float4 *>(ne)[j >> 1];
-                        const float d0 = fmaf(c.x, scr, __uint_as_float(v[j]));       // S' - offset' * 2^-e_row
-                        const float d1 = fmaf(c.z, scr, __uint_as_float(v[j + 1]));
-                        const float t0 = fabsf(d0) - (HOOK ? c.y * p.eb_scale : c.y); // < 0: the visit is ambiguous
-                        const float t1 = fabsf(d1) - (HOOK ? c.w * p.eb_scale : c.w);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 c = nt4[j >> 2];                                  // warp-uniform (broadcast) 16-byte load
+                        const float d0 = fmaf(c.x, scr, __uint_as_float(v[j]));        // S' - offset' * 2^-e_row
+                        const float d1 = fmaf(c.y, scr, __uint_as_float(v[j + 1]));
+                        const float d2 = fmaf(c.z, scr, __uint_as_float(v[j + 2]));
+                        const float d3 = fmaf(c.w, scr, __uint_as_float(v[j + 3]));
                         Lq[j >> 3] = __funnelshift_l(__float_as_uint(d0), Lq[j >> 3], 1);   // append the sign bits
-                        Aq[j >> 3] = __funnelshift_l(__float_as_uint(t0), Aq[j >> 3], 1);
                         Lq[j >> 3] = __funnelshift_l(__float_as_uint(d1), Lq[j >> 3], 1);
-                        Aq[j >> 3] = __funnelshift_l(__float_as_uint(t1), Aq[j >> 3], 1);
+                        Lq[j >> 3] = __funnelshift_l(__float_as_uint(d2), Lq[j >> 3], 1);
+                        Lq[j >> 3] = __funnelshift_l(__float_as_uint(d3), Lq[j >> 3], 1);
+                        mn = fmin3_abs(d0, d1, mn);
+                        mn = fmin3_abs(d2, d3, mn);
                     }
                     // column j of the chunk ends up in bit 31 - j
                     const uint32_t L = (Lq[0] << 24) | (Lq[1] << 16) | (Lq[2] << 8) | Lq[3];
-                    const uint32_t A = (Aq[0] << 24) | (Aq[1] << 16) | (Aq[2] << 8) | Aq[3];
+                    uint32_t A = 0;
+                    const float emax = HOOK ? M->emax[cc] * p.eb_scale : M->emax[cc];
+                    if (__any_sync(0xffffffffu, !(mn >= emax))) {
+                        const float2 *ne = M->ne + cc * 32;
+                        uint32_t Aq[4] = {0, 0, 0, 0};
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float2 c = ne[j];
+                            const float dlt = fmaf(c.x, scr, __uint_as_float(v[j]));
+                            const float tt = fabsf(dlt) - (HOOK ? c.y * p.eb_scale : c.y);   // < 0: the visit is ambiguous
+                            Aq[j >> 3] = __funnelshift_l(__float_as_uint(tt), Aq[j >> 3], 1);
+                        }
+                        A = (Aq[0] << 24) | (Aq[1] << 16) | (Aq[2] << 8) | Aq[3];
+                    }
                     mq[cc * 32 + lane] = make_uint2(L, (A | amb_or) & amb_and);
                     if (p.probe && tile == 0 && live) {
 #pragma unroll
@@ -662,6 +689,8 @@ __global__ void ext_tc_prepare_cols(const float *__restrict__ w, const int32_t *
         float bf = (float)bnd;
         if ((double)bf <= bnd) bf = nextafterf(bf, INFINITY);  // strictly above: the filter tests |dlt| - bound >= 0
         M->ne[col % BN] = make_float2(-thr, bf);
+        M->nthr[col % BN] = -thr;
+        atomicMax(reinterpret_cast<int *>(&M->emax[(col % BN) / 32]), __float_as_int(bf));   // positive floats order like ints
         if (bad) atomicExch(flag, 1);
     }
 }
@@ -819,8 +848,10 @@ int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const 
         std::memset(&m, 0, sizeof m);
         for (int i = 0; i < BN; i++) {
             m.ne[i] = make_float2(0.f, 0.f);
+            m.nthr[i] = INFINITY;   // padding columns never look ambiguous to the drain's chunk-wide test
             m.slot[i] = -1;
         }
+        for (int i = 0; i < BN / 32; i++) m.emax[i] = 0.f;
         for (int i = 0; i < MAX_NODES_PER_BLOCK; i++) m.next[i] = make_uint2((uint32_t)i, (uint32_t)i);
         m.tree0 = tree0;
         col_slot.resize(metas.size() * BN, -1);
