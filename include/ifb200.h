@@ -205,6 +205,13 @@ IFB_API int ifb_ext_tc_info(const ifb_forest *forest, int32_t *k_padded, int32_t
 IFB_API int ifb_ext_tc_probe(const ifb_forest *forest, const float *X, int64_t n_rows, int32_t d, int64_t ld,
                              int32_t layout, double *scores, float *acc_device, int32_t *col_slot_host, void *stream);
 
+/* Diagnostic of the rank-word path of standard forests (csrc/score_std_rank.cu; opt-in with IFB_STD_RANK=1 in the
+ * environment): matrices of d <= 32 features are scored on per-feature ranks (same decisions as
+ * IsolationTree.pathLength, IF/IsolationTree.scala:196-230).  *n_chunks = number of forest chunks of that layout for a
+ * matrix of d features (built on first use), 0 when the path is off or the forest / shape does not qualify and the f32
+ * kernel of score_std.cu scores it. */
+IFB_API int ifb_std_rank_info(const ifb_forest *forest, int32_t d, int32_t *n_chunks);
+
 /* prediction column: (score >= threshold) ? 1.0 : 0.0, all 0.0 when threshold <= 0
  * (IF/IsolationForestModel.scala:143-148). */
 IFB_API int ifb_predict_device(int32_t device, const double *scores, int64_t n_rows, double threshold,

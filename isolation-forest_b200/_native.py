@@ -85,6 +85,7 @@ SYMBOLS = {
     "ifb_peer_signal_device": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_uint32, C.c_void_p]),
     "ifb_peer_wait_device": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_uint32, C.c_void_p]),
     "ifb_ext_tc_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ifb_std_rank_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "ifb_ext_tc_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "ifb_predict_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
@@ -242,6 +243,12 @@ class NativeForest:
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         check(lib().ifb_score_device(self.handle, p(X), n, d, ld, layout, p(scores), p(dsum), p(psum), st))
         return (scores, dsum, psum) if want_parts else scores
+
+    def std_rank_chunks(self, d: int) -> int:
+        """Forest chunks of the rank-word layout for a matrix of d features; 0 = scored by the f32 kernel."""
+        n = C.c_int32(0)
+        check(lib().ifb_std_rank_info(self.handle, int(d), C.byref(n)))
+        return int(n.value)
 
     def ext_tc_info(self):
         """(padded hyperplane width, accumulator columns) of the tensor-core layout; (0, 0) when the forest has none."""

@@ -212,6 +212,18 @@ int ifb_ext_tc_info(const ifb_forest *f, int32_t *k_padded, int32_t *n_columns) 
     return IFB_OK;
 }
 
+int ifb_std_rank_info(const ifb_forest *f, int32_t d, int32_t *n_chunks) {
+    IFB_REQUIRE(f && n_chunks, "null argument");
+    *n_chunks = 0;
+    if (f->extended || d < 1 || d > 32 || f->num_trees == 0 || !std_rank_enabled()) return IFB_OK;
+    DeviceGuard dg(f->device);
+    RankPlan *rp = nullptr;
+    int rc = get_rank_plan(const_cast<ifb_forest *>(f), d, &rp);
+    if (rc) return rc;
+    *n_chunks = rank_plan_chunks(rp);
+    return IFB_OK;
+}
+
 int ifb_ext_tc_probe(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
                      double *scores, float *acc_device, int32_t *col_slot_host, void *stream) {
     int rc = check_scoring_args(f, X, n_rows, d, ld, layout);

@@ -638,6 +638,7 @@ ifb_forest::~ifb_forest() {
         cudaFree(p->d_tree_root);
         delete p;
     }
+    ifb::free_rank_plans(this);
     cudaFree(d_gval);
     cudaFree(d_gfeat);
     cudaFree(d_gchild);

@@ -84,6 +84,10 @@ struct WideNode {
 
 }  // namespace ifb
 
+namespace ifb {
+struct RankPlan;   // score_std_rank.cu
+}
+
 struct ifb_forest {
     int32_t device = 0;
     bool extended = false;
@@ -128,6 +132,7 @@ struct ifb_forest {
     };
     std::mutex plan_mu;
     std::vector<StdPlan *> std_plans;
+    std::vector<ifb::RankPlan *> rank_plans;   // rank-word tables for matrices of <= 32 features (score_std_rank.cu)
     // global-memory tables for the generic fallback kernel (rows too wide for a shared-memory plan); lazily built
     float *d_gval = nullptr;        // [nodes] BFS order: threshold (f32 ceil) or leaf value
     int32_t *d_gfeat = nullptr;     // [nodes] feature, -1 at leaves
@@ -217,6 +222,15 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
                           int32_t d, int64_t ld, int32_t layout, double *scores, int32_t *depth_sum,
                           float *path_sum, bool accumulate_only, cudaStream_t stream,
                           const ScatterTarget *scatter = nullptr);
+// score_std_rank.cu: the standard walk on per-feature ranks (opt-in with IFB_STD_RANK=1; d <= 32, finite thresholds,
+// no depth sums); a plan with rank_plan_chunks() == 0 means "does not qualify, use score_std.cu"
+bool std_rank_enabled();   // IFB_STD_RANK=1 (score_std.cu)
+int get_rank_plan(ifb_forest *f, int32_t d, RankPlan **out);
+int rank_plan_chunks(const RankPlan *rp);
+void free_rank_plans(ifb_forest *f);
+int launch_score_standard_rank(const ifb_forest *f, RankPlan *rp, const float *X, int64_t n_rows, int32_t d, int64_t ld,
+                               double *scores, float *path_sum, bool accumulate_only, cudaStream_t stream,
+                               const ScatterTarget *scatter);
 // score_ext.cu
 int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld,
                           int32_t layout, double *scores, int32_t *depth_sum, float *path_sum,

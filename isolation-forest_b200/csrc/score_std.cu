@@ -35,6 +35,10 @@ namespace ifb {
 // independently (see kGroupPipe in the kernel): 1024 -> 4 x 256, 512 -> 2 x 256.  Splitting 256-row tiles into
 // 2 x 128 was measured and LOSES 17 % (d = 128: 128-row boxes halve the contiguous run of every TMA row), so tiles of
 // <= 256 rows keep one box and whole-tile refills.  IFB_STD_NO_GROUPS=1 (A/B hook) restores whole-tile refills.
+bool std_rank_enabled() {
+    const char *e = getenv("IFB_STD_RANK");   // read on every call: tests switch it inside one process
+    return e != nullptr && e[0] == '1';
+}
 bool std_grouped() {
     static const bool v = getenv("IFB_STD_NO_GROUPS") == nullptr;
     return v;
@@ -88,6 +92,7 @@ struct ScoreStdParams {
     int32_t *depth_sum;      // may be null
     int64_t n_tiles;
     ScatterTarget scatter;   // tree-sharded multi-GPU: where the finished per-row sums of the LAST chunk go
+    int32_t l2_prefetch;     // single-stage whole-tile refills: prefetch the next tile into L2 during the walk
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,6 +130,14 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "[%4];" ::"r"(smem_u32(dst)),
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
+}
+
+// L2 prefetch of a box (no shared-memory destination, no barrier): used by single-stage tiles that cannot overlap
+// their refill with the walk -- the next tile is pulled into L2 while this one is walked, so the refill itself runs
+// at L2 speed instead of waiting on HBM.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1)
+                 : "memory");
 }
 
 // Shared-memory carve-up (byte offsets from the dynamic smem base, which is 1024-aligned).
@@ -239,6 +252,18 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
         }
     };
 
+    auto prefetch_tile = [&](int64_t tile) {
+        // thread 0 only: the boxes issue_tile(tile, .) will fetch, pulled into L2 ahead of time
+        const int64_t row0 = tile * R;
+#pragma unroll
+        for (int sub = 0; sub < NSUB; sub++) {
+            const int32_t r0 = (int32_t)(row0 + (int64_t)sub * RB);
+            int f = 0;
+            for (; f + p.box_d <= d; f += p.box_d) tma_prefetch_2d(&tmap_main, r0, f);
+            if (p.rem_d) tma_prefetch_2d(&tmap_rem, r0, f);
+        }
+    };
+
     auto issue_group = [&](int64_t tile, int sub) {
         // called by the first thread of row group `sub` (kGroupPipe): refill this group's sub-tile only
         float *sdst = reinterpret_cast<float *>(smem + L.tiles) + (uint32_t)sub * sub_floats;
@@ -277,6 +302,9 @@ score_std_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_con
         } else {
             load_tile_plain(tile, stage);
             __syncthreads();
+        }
+        if constexpr (USE_TMA && kStages == 1 && !kGroupPipe) {
+            if (p.l2_prefetch && tid == 0 && tile + stride < p.n_tiles) prefetch_tile(tile + stride);
         }
         const uint32_t xrow_s = tiles_s + ((uint32_t)stage * tile_floats + (uint32_t)sub * sub_floats + (uint32_t)rl) * 4u;
         const int64_t row = tile * R + tid;
@@ -518,6 +546,16 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
                           bool accumulate_only, cudaStream_t stream, const ScatterTarget *scatter) {
     IFB_REQUIRE(layout == IFB_COL_MAJOR, "launch_score_standard expects a column-major matrix");
     if (n_rows == 0) return IFB_OK;
+    // IFB_STD_RANK=1 (opt-in, measured alternative): narrow matrices walk on per-feature ranks (score_std_rank.cu).
+    // Not the default: 2.53 ms against 2.48 ms for config 2 (DESIGN.md 4.1b has the ncu breakdown).
+    if (!depth_sum && d <= 32 && std_rank_enabled()) {
+        RankPlan *rp = nullptr;
+        int rc = get_rank_plan(const_cast<ifb_forest *>(f), d, &rp);
+        if (rc) return rc;
+        const int nc = rank_plan_chunks(rp);
+        if (nc == 1 || (nc > 1 && (path_sum != nullptr || accumulate_only)))
+            return launch_score_standard_rank(f, rp, X, n_rows, d, ld, scores, path_sum, accumulate_only, stream, scatter);
+    }
     const int R = plan->rows_per_tile;
     const int RB = std_rows_per_box(R, plan->stages);
     const bool want_depth = depth_sum != nullptr;
@@ -570,6 +608,8 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
         p.n_tiles = n_tiles;
         if (scatter) p.scatter = *scatter; else p.scatter.world = 0;
         p.finalize_scatter = (scatter && ci + 1 == n_chunks) ? 1 : 0;
+        static const bool no_prefetch = getenv("IFB_STD_NO_L2_PREFETCH") != nullptr;
+        p.l2_prefetch = no_prefetch ? 0 : 1;
         const int S = plan->stages;
         const SmemLayout L = make_layout(p.n_trees, p.chunk_words, R, d, S);
         const TopTable &top = *reinterpret_cast<const TopTable *>(plan->h_top.data() + (size_t)ci * sizeof(TopTable));
@@ -586,10 +626,13 @@ int launch_score_standard(const ifb_forest *f, ifb_forest::StdPlan *plan, const 
                 rc = S == 2 ? launch_variant<512, 4, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
                             : launch_variant<512, 4, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream);
                 break;
-            case 256:
-                rc = S == 2 ? launch_variant<256, 8, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
-                            : launch_variant<256, 8, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream);
+            case 256: {
+                static const int c256 = getenv("IFB_STD_256") ? atoi(getenv("IFB_STD_256")) : 16;
+                rc = S == 2     ? launch_variant<256, 8, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
+                   : c256 == 16 ? launch_variant<256, 16, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
+                                : launch_variant<256, 8, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream);
                 break;
+            }
             case 128:
                 rc = S == 2 ? launch_variant<128, 16, 2>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream)
                             : launch_variant<128, 16, 1>(use_tma, want_depth, m0, m1, top, p, grid, L.total, stream);
