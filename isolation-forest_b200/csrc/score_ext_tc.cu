@@ -54,14 +54,9 @@ constexpr int MAX_LEAVES_PER_BLOCK = 256;   // node ids stay below 512: bit 8 al
 constexpr uint32_t A_BYTES = BM * BK * 2;   //  8 KB
 constexpr uint32_t B_BYTES = BN * BK * 2;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl: 48 KB
-#ifndef IFB_TC_EPI_WARPS
-#define IFB_TC_EPI_WARPS 16
-#endif
-constexpr int EPI_WARPS = IFB_TC_EPI_WARPS;   // 8 or 16
-constexpr int QW = EPI_WARPS / 4;             // epilogue warps per TMEM lane quarter
-static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "two or four epilogue warps per lane quarter");
+constexpr int EPI_WARPS = 16;    // four per TMEM lane quarter (= per scheduler): two pairs working on alternate blocks
 constexpr int META_RING = 3;     // block descriptors in flight: the producer runs ahead of the epilogue by up to 3 blocks
-constexpr int THREADS = (2 + EPI_WARPS) * 32;
+constexpr int THREADS = (2 + EPI_WARPS + 1) * 32;   // producer, MMA issuer, 16 epilogue warps, summing warp
 
 // Node ids inside a block: [0, 256) = internal nodes (= accumulator columns), 256 + i = leaf i of the block.
 constexpr uint32_t LEAF0 = BN;
@@ -87,12 +82,12 @@ constexpr uint32_t META_BYTES = sizeof(BlockMeta);
 
 // shared-memory carve-up (offsets from a 1024-aligned base)
 constexpr uint32_t OFF_STAGES = 0;
-constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;          // per lane quarter: {left, ambiguous} words [8][32]
-constexpr uint32_t OFF_LV = OFF_MASKS + 4 * 2048;                          // [2][MAX_TREES_PER_BLOCK][128] leaf values
-constexpr uint32_t OFF_DSX = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;    // [3][128] depth counts of warps 1.. of a quarter
-constexpr uint32_t OFF_META = OFF_DSX + 3 * BM * 4;
+constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;          // [2 pairs][4 quarters]: {left, ambiguous} words [8][32]
+constexpr uint32_t OFF_LV = OFF_MASKS + 8 * 2048;                          // [2][MAX_TREES_PER_BLOCK][128] leaf values
+constexpr uint32_t OFF_LD = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;     // [2][MAX_TREES_PER_BLOCK][128] leaf depths (u8)
+constexpr uint32_t OFF_META = OFF_LD + 2 * MAX_TREES_PER_BLOCK * BM;
 constexpr uint32_t OFF_BARS = (OFF_META + META_RING * META_BYTES + 15u) & ~15u;
-constexpr int NBARS = 2 * STAGES + 4 + 2 * META_RING;
+constexpr int NBARS = 2 * STAGES + 4 + 2 * META_RING + 4;
 constexpr uint32_t OFF_TMEMPTR = OFF_BARS + NBARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;   // + alignment slack
 
@@ -297,6 +292,8 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     auto bar_tempty = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 2 + b); };
     auto bar_mfull = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 4 + b); };
     auto bar_mempty = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 4 + META_RING + b); };
+    auto bar_lvfull = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 4 + 2 * META_RING + b); };
+    auto bar_lvempty = [&](int b) { return bars + 8u * (uint32_t)(2 * STAGES + 4 + 2 * META_RING + 2 + b); };
     uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(sm + OFF_TMEMPTR);
 
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
@@ -308,11 +305,13 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(bar_tfull(b), 1);
-            mbar_init(bar_tempty(b), EPI_WARPS);
+            mbar_init(bar_tempty(b), EPI_WARPS / 2);    // the eight warps of the pair that owns this accumulator buffer
+            mbar_init(bar_lvfull(b), EPI_WARPS / 2);
+            mbar_init(bar_lvempty(b), 1);               // the summing warp
         }
         for (int b = 0; b < META_RING; b++) {
             mbar_init(bar_mfull(b), 1);
-            mbar_init(bar_mempty(b), EPI_WARPS);
+            mbar_init(bar_mempty(b), EPI_WARPS / 2 + 1);   // the block's eight epilogue warps + the summing warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -411,16 +410,73 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 }
             }
         }
+    } else if (warp == 2 + EPI_WARPS) {
+        // ===== summing warp: adds the leaf values of every block in tree order, owns the per-row results =====
+        // lane l owns rows l, l + 32, l + 64, l + 96 of the tile.  Taking the sums out of the walking warps lets the two
+        // halves of a lane quarter's warps work on alternate blocks without handing a running sum back and forth.
+        const float *lvbuf = reinterpret_cast<const float *>(sm + OFF_LV);
+        const uint8_t *ldbuf = reinterpret_cast<const uint8_t *>(sm + OFF_LD);
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            float s[4];
+            int32_t ds[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t row = tile * BM + j * 32 + lane;
+                const bool live = row < p.n_rows;
+                s[j] = (p.accumulate_only && live) ? p.path_sum[row] : 0.f;
+                ds[j] = (p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
+            }
+            for (int b = 0; b < NB; b++, it++) {
+                const int buf = (int)(it & 1u);
+                const int mb = (int)(it % META_RING);
+                mbar_wait(bar_mfull(mb), (it / META_RING) & 1u);
+                const int nt = reinterpret_cast<const BlockMeta *>(sm + OFF_META + (uint32_t)mb * META_BYTES)->n_trees;
+                mbar_wait(bar_lvfull(buf), (it >> 1) & 1u);
+                const float *lv = lvbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + lane;
+                const uint8_t *ld = ldbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + lane;
+                for (int t = 0; t < nt; t++) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        s[j] = s[j] + lv[t * BM + j * 32];   // tree order, one f32 add per tree (Array[Float].sum)
+                        ds[j] += (int32_t)ld[t * BM + j * 32];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar_lvempty(buf));
+                    mbar_arrive(bar_mempty(mb));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t row = tile * BM + j * 32 + lane;
+                if (row < p.n_rows) {
+                    if (!p.accumulate_only) {
+                        // IF/extended/ExtendedIsolationForestModel.scala:116-119: Float sum / Int, -Float / Float, Math.pow(2, Double)
+                        const float e = __fdiv_rn(s[j], (float)p.total_trees);
+                        const float z = __fdiv_rn(-e, p.avg_path);
+                        p.scores[row] = exp2((double)z);
+                    }
+                    if (p.path_sum) p.path_sum[row] = s[j];
+                    if (p.depth_sum) p.depth_sum[row] = ds[j];
+                }
+            }
+        }
     } else {
         // ===== epilogue warps: TMEM -> registers -> decision masks -> tree walks =====
         const int ew = warp - 2;                 // 0..15
-        const int q = warp & 3;                  // TMEM lane quarter this warp may access (rows q*32 .. q*32+31 of the tile)
-        const int gi = ew >> 2;                  // position in the quad of warps that share the quarter
-        // [8 chunks][32 lanes] {"left" bits, "ambiguous" bits}: column j of a chunk sits in bit 31 - j of both words
-        uint2 *mq = reinterpret_cast<uint2 *>(sm + OFF_MASKS + (uint32_t)q * 2048u);
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access (rows q*32 .. q*32+31 of the tile);
+                                                 // it is also the warp's scheduler, so the four warps of a quarter share one
+        const int gi = ew >> 2;                  // position among the four warps of the quarter
+        const int pair = gi >> 1;                // the quarter's warps work in two PAIRS on alternate blocks: while one pair
+        const int pi = gi & 1;                   // walks (latency-bound), the other drains (issue-bound) on the same scheduler
+        // per pair and quarter: [8 chunks][32 lanes] {"left" bits, "ambiguous" bits}; column j of a chunk = bit 31 - j
+        uint2 *mq = reinterpret_cast<uint2 *>(sm + OFF_MASKS + (uint32_t)(pair * 4 + q) * 2048u);
         float *lvbuf = reinterpret_cast<float *>(sm + OFF_LV);
-        int32_t *dsx = reinterpret_cast<int32_t *>(sm + OFF_DSX);
-        const int quad_bar = 1 + q;              // named barrier of the four warps that share this lane quarter
+        uint8_t *ldbuf = reinterpret_cast<uint8_t *>(sm + OFF_LD);
+        const int pair_bar = 1 + q * 2 + pair;   // named barrier of the two warps of this pair and quarter
+        const int buf = pair;                    // blocks with (it & 1) == pair: accumulator / leaf-value buffer `pair`
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t row = tile * BM + q * 32 + lane;
@@ -429,10 +485,8 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             const uint32_t flag = live ? (uint32_t)__ldg(p.rflag + row) : 1u;   // dead lanes behave like zero rows
             const uint32_t amb_or = flag == 2u ? 0xFFFFFFFFu : 0u;               // out-of-range row: everything ambiguous
             const uint32_t amb_and = flag == 1u ? 0u : 0xFFFFFFFFu;              // zero row: S' = 0 exactly, never ambiguous
-            float s = (gi == 0 && p.accumulate_only && live) ? p.path_sum[row] : 0.f;
-            int32_t dsum = (gi == 0 && p.accumulate_only && live && p.depth_sum) ? p.depth_sum[row] : 0;
             for (int b = 0; b < NB; b++, it++) {
-                const int buf = (int)(it & 1u);
+                if ((int)(it & 1u) != pair) continue;
                 const int mb = (int)(it % META_RING);
                 mbar_wait(bar_mfull(mb), (it / META_RING) & 1u);
                 mbar_wait(bar_tfull(buf), (it >> 1) & 1u);
@@ -440,9 +494,9 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 const BlockMeta *M = reinterpret_cast<const BlockMeta *>(sm + OFF_META + (uint32_t)mb * META_BYTES);
                 const int nt = M->n_trees;
                 const int nchunks = (M->n_cols + 31) >> 5;
-                // ---- drain, split by columns: this warp's two 32-column chunks -> two bits per accumulator ----
-                constexpr int CPW = 8 / QW;   // chunks per warp
-                for (int cc = gi * CPW; cc < nchunks && cc < gi * CPW + CPW; cc++) {
+                // ---- drain, split by columns: this warp's four 32-column chunks -> two bits per accumulator ----
+                constexpr int CPW = 4;   // chunks per warp
+                for (int cc = pi * CPW; cc < nchunks && cc < pi * CPW + CPW; cc++) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cc * 32);
                     uint32_t v[32];
                     tmem_ld32(taddr, v);
@@ -493,15 +547,18 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty(buf));
-                asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * QW) : "memory");   // the quad's 16 mask words are complete
-                // ---- walk, split by trees: trees gi, gi + 4, gi + 8, ... of the block, up to four chains per lane ----
+                asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(64) : "memory");   // the pair's 8 mask words are complete
+                // the summing warp has consumed the leaf values this buffer held two blocks ago
+                mbar_wait(bar_lvempty(buf), ((it >> 1) & 1u) ^ 1u);
+                // ---- walk, split by trees: trees pi, pi + 2, pi + 4, ... of the block, up to four chains per lane ----
                 float *lv = lvbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + q * 32 + lane;
-                auto walk_group = [&](auto nch_tag, int t0) {   // trees t0 + gi + QW * c, c < NCH
+                uint8_t *ld = ldbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + q * 32 + lane;
+                auto walk_group = [&](auto nch_tag, int t0) {   // trees t0 + pi + 2 * c, c < NCH
                     constexpr int NCH = decltype(nch_tag)::value;
                     uint32_t cur[NCH], amb[NCH];
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
-                        cur[c] = live ? (uint32_t)M->root[t0 + gi + QW * c] : LEAF0;
+                        cur[c] = live ? (uint32_t)M->root[t0 + pi + 2 * c] : LEAF0;
                         amb[c] = 0;
                     }
                     // fast path: branch-free levels that ignore ambiguity and only remember (bit 31 of amb) whether an
@@ -527,7 +584,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         // (lane, chain) at a time, the whole warp cooperating
                         uint32_t stuck = 0;
 #pragma unroll
-                        for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[t0 + gi + QW * c] : LEAF0;
+                        for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[t0 + pi + 2 * c] : LEAF0;
                         while (true) {
 #pragma unroll 1
                             for (int lvl = 0; lvl < p.max_depth; lvl++) {
@@ -571,14 +628,14 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
                         const uint32_t lf = cur[c] - LEAF0;
-                        lv[(t0 + gi + QW * c) * BM] = M->leafv[lf];
-                        dsum += (int32_t)M->leafd[lf];
+                        lv[(t0 + pi + 2 * c) * BM] = M->leafv[lf];
+                        ld[(t0 + pi + 2 * c) * BM] = M->leafd[lf];
                     }
                 };
-                const int my_trees = nt > gi ? (nt - gi + QW - 1) / QW : 0;   // <= MAX_TREES_PER_BLOCK / QW
+                const int my_trees = nt > pi ? (nt - pi + 1) / 2 : 0;   // <= MAX_TREES_PER_BLOCK / 2
                 for (int done = 0; done < my_trees;) {
                     const int left_trees = my_trees - done;
-                    const int t0 = done * QW;
+                    const int t0 = done * 2;
                     if (left_trees >= 4) {
                         walk_group(std::integral_constant<int, 4>{}, t0);
                         done += 4;
@@ -593,30 +650,15 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         done += 1;
                     }
                 }
-                // ---- the quad meets again; its first warp adds the block's leaf values in tree order ----
-                asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * QW) : "memory");
-                if (gi == 0) {
-                    for (int t = 0; t < nt; t++) s = s + lv[t * BM];
-                }
+                // leaf values and depths of this warp's trees are in shared memory: hand them to the summing warp
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_mempty(mb));
-            }
-            // depth counts of the quad's other warps travel through shared memory
-            if (gi > 0) dsx[(gi - 1) * BM + q * 32 + lane] = dsum;
-            asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * QW) : "memory");
-            if (gi == 0 && live) {
-#pragma unroll
-                for (int w = 0; w < QW - 1; w++) dsum += dsx[w * BM + q * 32 + lane];
-                if (!p.accumulate_only) {
-                    // IF/extended/ExtendedIsolationForestModel.scala:116-119: Float sum / Int, -Float / Float, Math.pow(2, Double)
-                    const float e = __fdiv_rn(s, (float)p.total_trees);
-                    const float z = __fdiv_rn(-e, p.avg_path);
-                    p.scores[row] = exp2((double)z);
+                if (lane == 0) {
+                    mbar_arrive(bar_lvfull(buf));
+                    mbar_arrive(bar_mempty(mb));
                 }
-                if (p.path_sum) p.path_sum[row] = s;
-                if (p.depth_sum) p.depth_sum[row] = dsum;
+                // the pair's mask words may be overwritten (next drain) only when both warps are done walking on them
+                asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(64) : "memory");
             }
-            asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "n"(32 * QW) : "memory");   // dsx is free for the next tile
         }
     }
     tc_fence_before();
