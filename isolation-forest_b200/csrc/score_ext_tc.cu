@@ -54,9 +54,13 @@ constexpr int MAX_LEAVES_PER_BLOCK = 256;   // node ids stay below 512: bit 8 al
 constexpr uint32_t A_BYTES = BM * BK * 2;   //  8 KB
 constexpr uint32_t B_BYTES = BN * BK * 2;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl: 48 KB
-constexpr int EPI_WARPS = 16;    // four per TMEM lane quarter (= per scheduler): two pairs working on alternate blocks
+#ifndef IFB_TC_PW
+#define IFB_TC_PW 2
+#endif
+constexpr int PW = IFB_TC_PW;    // warps per team: a lane quarter (= scheduler) has two teams working on alternate blocks
+constexpr int EPI_WARPS = 8 * PW;
 constexpr int META_RING = 3;     // block descriptors in flight: the producer runs ahead of the epilogue by up to 3 blocks
-constexpr int THREADS = (2 + EPI_WARPS + 1) * 32;   // producer, MMA issuer, 16 epilogue warps, summing warp
+constexpr int THREADS = (2 + EPI_WARPS + 2) * 32;   // producer, MMA issuer, 16 epilogue warps, summing warp, descriptor loader
 
 // Node ids inside a block: [0, 256) = internal nodes (= accumulator columns), 256 + i = leaf i of the block.
 constexpr uint32_t LEAF0 = BN;
@@ -129,33 +133,50 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // Bounded wait: a lost transaction / bad descriptor must surface as a launch failure, never as a hung GPU
 // (wall-clock bound of ~4 s on %globaltimer; the longest legitimate wait is one block of MMAs, tens of microseconds).
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-    // the suspend-time hint lets the hardware park the thread until the phase completes (or the hint expires) instead
-    // of returning early: a waiting role then costs no issue slots of the scheduler it shares with the epilogue warps
+// The polling loop itself is three instructions (try_wait blocks in hardware for a system-dependent time before it
+// reports "not yet"): an earlier version polled through a 13-instruction C loop and its spinning warps ate 30 % of the
+// issue slots -- and, being ALU instructions, of the pipe the epilogue is bound by (profiles/r02_score_ext_tc_v10_ncu.md).
+__device__ __forceinline__ bool mbar_poll(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0x10000;\n"
+        "IFB_TC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "@p bra IFB_TC_DONE_%=;\n"
+        "sub.u32 n, n, 1;\n"
+        "setp.ne.u32 p, n, 0;\n"
+        "@p bra IFB_TC_WAIT_%=;\n"
+        "setp.ne.u32 p, n, 0;\n"          // n == 0: gave up after 65536 polls -> p = false
+        "IFB_TC_DONE_%=:\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(200000u)
+        : "r"(bar), "r"(parity)
         : "memory");
     return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try(bar, parity)) return;
+    if (mbar_poll(bar, parity)) return;
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (uint32_t spin = 1;; ++spin) {
-        if (mbar_try(bar, parity)) return;
-        if ((spin & 1023u) == 0) {
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ull) __trap();
-        }
+    while (!mbar_poll(bar, parity)) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) __trap();
     }
+}
+// diagnostic variant (IFB_TC_STATS): adds the cycles spent in the wait to *acc
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, unsigned long long *acc, bool on) {
+    if (!on) {
+        mbar_wait(bar, parity);
+        return;
+    }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    *acc += (unsigned long long)(clock64() - t0);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int32_t c0, int32_t c1, uint32_t bar) {
     asm volatile(
@@ -338,15 +359,13 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
+            const bool st_on = p.stats != nullptr;
+            unsigned long long w_mempty = 0, w_empty = 0;
+            const long long t_begin = clock64();
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int b = 0; b < NB; b++, it++) {
-                    const int mb = (int)(it % META_RING);
-                    mbar_wait(bar_mempty(mb), ((it / META_RING) & 1u) ^ 1u);
-                    mbar_expect_tx(bar_mfull(mb), META_BYTES);
-                    bulk_g2s(base + OFF_META + (uint32_t)mb * META_BYTES, p.meta + (size_t)b * META_BYTES, META_BYTES,
-                             bar_mfull(mb));
                     for (int kc = 0; kc < KC; kc++) {
-                        mbar_wait(bar_empty(stage), phase ^ 1u);
+                        mbar_wait_timed(bar_empty(stage), phase ^ 1u, &w_empty, st_on);
                         const uint32_t st = base + OFF_STAGES + (uint32_t)stage * STAGE_BYTES;
                         mbar_expect_tx(bar_full(stage), STAGE_BYTES);
                         tma_load_2d(st, &map_xh, kc * BK, (int32_t)(tile * BM), bar_full(stage));
@@ -370,6 +389,11 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                     }
                 }
             }
+            if (st_on) {
+                atomicAdd(p.stats + 1, w_mempty);
+                atomicAdd(p.stats + 2, w_empty);
+                atomicAdd(p.stats + 3, (unsigned long long)(clock64() - t_begin));
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread issues for the whole CTA =====
@@ -378,14 +402,17 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
+            const bool st_on = p.stats != nullptr;
+            unsigned long long w_tempty = 0, w_full = 0;
+            const long long t_begin = clock64();
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int b = 0; b < NB; b++, it++) {
                     const int buf = (int)(it & 1u);
-                    mbar_wait(bar_tempty(buf), ((it >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
+                    mbar_wait_timed(bar_tempty(buf), ((it >> 1) & 1u) ^ 1u, &w_tempty, st_on);   // the epilogue has drained this accumulator buffer
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
                     for (int kc = 0; kc < KC; kc++) {
-                        mbar_wait(bar_full(stage), phase);
+                        mbar_wait_timed(bar_full(stage), phase, &w_full, st_on);
                         tc_fence_after();
                         const uint32_t st = base + OFF_STAGES + (uint32_t)stage * STAGE_BYTES;
 #pragma unroll
@@ -407,6 +434,26 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         }
                     }
                     umma_commit(bar_tfull(buf));   // accumulators of this block are complete
+                }
+            }
+            if (st_on) {
+                atomicAdd(p.stats + 4, w_tempty);
+                atomicAdd(p.stats + 5, w_full);
+                atomicAdd(p.stats + 6, (unsigned long long)(clock64() - t_begin));
+            }
+        }
+    } else if (warp == 3 + EPI_WARPS) {
+        // ===== descriptor loader: block descriptors (node tables of the walk) into their ring, independent of the operand
+        // stages -- a descriptor slot is only released after the block's walk, which must not hold back operand loads =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int b = 0; b < NB; b++, it++) {
+                    const int mb = (int)(it % META_RING);
+                    mbar_wait(bar_mempty(mb), ((it / META_RING) & 1u) ^ 1u);
+                    mbar_expect_tx(bar_mfull(mb), META_BYTES);
+                    bulk_g2s(base + OFF_META + (uint32_t)mb * META_BYTES, p.meta + (size_t)b * META_BYTES, META_BYTES,
+                             bar_mfull(mb));
                 }
             }
         }
@@ -468,9 +515,9 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         const int ew = warp - 2;                 // 0..15
         const int q = warp & 3;                  // TMEM lane quarter this warp may access (rows q*32 .. q*32+31 of the tile);
                                                  // it is also the warp's scheduler, so the four warps of a quarter share one
-        const int gi = ew >> 2;                  // position among the four warps of the quarter
-        const int pair = gi >> 1;                // the quarter's warps work in two PAIRS on alternate blocks: while one pair
-        const int pi = gi & 1;                   // walks (latency-bound), the other drains (issue-bound) on the same scheduler
+        const int gi = ew >> 2;                  // position among the 2 * PW warps of the quarter
+        const int pair = gi / PW;                // the quarter's warps work in two TEAMS on alternate blocks: while one team
+        const int pi = gi % PW;                  // walks (latency-bound), the other drains (issue-bound) on the same scheduler
         // per pair and quarter: [8 chunks][32 lanes] {"left" bits, "ambiguous" bits}; column j of a chunk = bit 31 - j
         uint2 *mq = reinterpret_cast<uint2 *>(sm + OFF_MASKS + (uint32_t)(pair * 4 + q) * 2048u);
         float *lvbuf = reinterpret_cast<float *>(sm + OFF_LV);
@@ -478,6 +525,9 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         const int pair_bar = 1 + q * 2 + pair;   // named barrier of the two warps of this pair and quarter
         const int buf = pair;                    // blocks with (it & 1) == pair: accumulator / leaf-value buffer `pair`
         uint32_t it = 0;
+        const bool st_on = p.stats != nullptr;   // diagnostic cycle accounts (IFB_TC_STATS), reported by warp 2 of each CTA
+        unsigned long long w_mfull = 0, w_tfull = 0, w_lvempty = 0, c_drain = 0, c_walk = 0;
+        const long long t_begin = st_on ? clock64() : 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t row = tile * BM + q * 32 + lane;
             const bool live = row < p.n_rows;
@@ -488,15 +538,15 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             for (int b = 0; b < NB; b++, it++) {
                 if ((int)(it & 1u) != pair) continue;
                 const int mb = (int)(it % META_RING);
-                mbar_wait(bar_mfull(mb), (it / META_RING) & 1u);
-                mbar_wait(bar_tfull(buf), (it >> 1) & 1u);
+                mbar_wait_timed(bar_mfull(mb), (it / META_RING) & 1u, &w_mfull, st_on);
+                mbar_wait_timed(bar_tfull(buf), (it >> 1) & 1u, &w_tfull, st_on);
                 tc_fence_after();
+                const long long t_drain0 = st_on ? clock64() : 0;
                 const BlockMeta *M = reinterpret_cast<const BlockMeta *>(sm + OFF_META + (uint32_t)mb * META_BYTES);
                 const int nt = M->n_trees;
                 const int nchunks = (M->n_cols + 31) >> 5;
                 // ---- drain, split by columns: this warp's four 32-column chunks -> two bits per accumulator ----
-                constexpr int CPW = 4;   // chunks per warp
-                for (int cc = pi * CPW; cc < nchunks && cc < pi * CPW + CPW; cc++) {
+                for (int cc = pi; cc < nchunks; cc += PW) {   // chunks pi, pi + PW, ...
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cc * 32);
                     uint32_t v[32];
                     tmem_ld32(taddr, v);
@@ -547,18 +597,20 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty(buf));
-                asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(64) : "memory");   // the pair's 8 mask words are complete
+                if (st_on) c_drain += (unsigned long long)(clock64() - t_drain0);
+                asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * PW) : "memory");   // the team's 8 mask words are complete
                 // the summing warp has consumed the leaf values this buffer held two blocks ago
-                mbar_wait(bar_lvempty(buf), ((it >> 1) & 1u) ^ 1u);
-                // ---- walk, split by trees: trees pi, pi + 2, pi + 4, ... of the block, up to four chains per lane ----
+                mbar_wait_timed(bar_lvempty(buf), ((it >> 1) & 1u) ^ 1u, &w_lvempty, st_on);
+                const long long t_walk0 = st_on ? clock64() : 0;
+                // ---- walk, split by trees: trees pi, pi + PW, pi + 2 PW, ... of the block, up to four chains per lane ----
                 float *lv = lvbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + q * 32 + lane;
                 uint8_t *ld = ldbuf + (size_t)buf * (MAX_TREES_PER_BLOCK * BM) + q * 32 + lane;
-                auto walk_group = [&](auto nch_tag, int t0) {   // trees t0 + pi + 2 * c, c < NCH
+                auto walk_group = [&](auto nch_tag, int t0) {   // trees t0 + pi + PW * c, c < NCH
                     constexpr int NCH = decltype(nch_tag)::value;
                     uint32_t cur[NCH], amb[NCH];
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
-                        cur[c] = live ? (uint32_t)M->root[t0 + pi + 2 * c] : LEAF0;
+                        cur[c] = live ? (uint32_t)M->root[t0 + pi + PW * c] : LEAF0;
                         amb[c] = 0;
                     }
                     // fast path: branch-free levels that ignore ambiguity and only remember (bit 31 of amb) whether an
@@ -584,7 +636,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         // (lane, chain) at a time, the whole warp cooperating
                         uint32_t stuck = 0;
 #pragma unroll
-                        for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[t0 + pi + 2 * c] : LEAF0;
+                        for (int c = 0; c < NCH; c++) cur[c] = live ? (uint32_t)M->root[t0 + pi + PW * c] : LEAF0;
                         while (true) {
 #pragma unroll 1
                             for (int lvl = 0; lvl < p.max_depth; lvl++) {
@@ -628,14 +680,14 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
                         const uint32_t lf = cur[c] - LEAF0;
-                        lv[(t0 + pi + 2 * c) * BM] = M->leafv[lf];
-                        ld[(t0 + pi + 2 * c) * BM] = M->leafd[lf];
+                        lv[(t0 + pi + PW * c) * BM] = M->leafv[lf];
+                        ld[(t0 + pi + PW * c) * BM] = M->leafd[lf];
                     }
                 };
-                const int my_trees = nt > pi ? (nt - pi + 1) / 2 : 0;   // <= MAX_TREES_PER_BLOCK / 2
+                const int my_trees = nt > pi ? (nt - pi + PW - 1) / PW : 0;   // <= MAX_TREES_PER_BLOCK / PW
                 for (int done = 0; done < my_trees;) {
                     const int left_trees = my_trees - done;
-                    const int t0 = done * 2;
+                    const int t0 = done * PW;
                     if (left_trees >= 4) {
                         walk_group(std::integral_constant<int, 4>{}, t0);
                         done += 4;
@@ -650,6 +702,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         done += 1;
                     }
                 }
+                if (st_on) c_walk += (unsigned long long)(clock64() - t_walk0);
                 // leaf values and depths of this warp's trees are in shared memory: hand them to the summing warp
                 __syncwarp();
                 if (lane == 0) {
@@ -657,8 +710,16 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                     mbar_arrive(bar_mempty(mb));
                 }
                 // the pair's mask words may be overwritten (next drain) only when both warps are done walking on them
-                asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(64) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * PW) : "memory");
             }
+        }
+        if (st_on && ew == 0 && lane == 0) {
+            atomicAdd(p.stats + 7, w_mfull);
+            atomicAdd(p.stats + 8, w_tfull);
+            atomicAdd(p.stats + 9, w_lvempty);
+            atomicAdd(p.stats + 10, c_drain);
+            atomicAdd(p.stats + 11, c_walk);
+            atomicAdd(p.stats + 12, (unsigned long long)(clock64() - t_begin));
         }
     }
     tc_fence_before();
@@ -1014,14 +1075,14 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     } scr{stream};
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_h = al((size_t)chunk * kp * 2), b_f = al((size_t)chunk * kp * 4), b_n = al((size_t)chunk * 4);
-    IFB_CUDA(cudaMallocAsync(&scr.p, 2 * b_h + b_f + 2 * b_n + 256, stream));
+    IFB_CUDA(cudaMallocAsync(&scr.p, 2 * b_h + b_f + 2 * b_n + 512, stream));
     unsigned char *a = reinterpret_cast<unsigned char *>(scr.p);
     __half *xh = reinterpret_cast<__half *>(a), *xl = reinterpret_cast<__half *>(a + b_h);
     float *xr = reinterpret_cast<float *>(a + 2 * b_h);
     float *rscale = reinterpret_cast<float *>(a + 2 * b_h + b_f);
     uint8_t *rflag = reinterpret_cast<uint8_t *>(a + 2 * b_h + b_f + b_n);
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(a + 2 * b_h + b_f + 2 * b_n);
-    if (want_stats) IFB_CUDA(cudaMemsetAsync(stats, 0, 8, stream));
+    if (want_stats) IFB_CUDA(cudaMemsetAsync(stats, 0, 128, stream));
 
     // CTAs per cluster sharing the hyperplane tiles by TMA multicast (IFB_TC_CLUSTER = 1 | 2 | 4 overrides).  Wide
     // hyperplanes are operand-feed bound (measured, 1M x 1024, 256 trees: 96.6 / 91.2 / 84.6 ms with 1 / 2 / 4 CTAs
@@ -1119,11 +1180,18 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
         count_launch();
     }
     if (want_stats) {
-        unsigned long long h = 0;
-        IFB_CUDA(cudaMemcpyAsync(&h, stats, 8, cudaMemcpyDeviceToHost, stream));
+        unsigned long long h[16] = {0};
+        IFB_CUDA(cudaMemcpyAsync(h, stats, 128, cudaMemcpyDeviceToHost, stream));
         IFB_CUDA(cudaStreamSynchronize(stream));
-        fprintf(stderr, "[ifb] tensor-core path: %llu visits decided exactly (rows %lld, trees %d)\n", h, (long long)n_rows,
+        fprintf(stderr, "[ifb] tensor-core path: %llu visits decided exactly (rows %lld, trees %d)\n", h[0], (long long)n_rows,
                 f->num_trees);
+        // cycle accounts summed over the CTAs of the last row chunk (one producer lane, one MMA lane, epilogue warp 2 each)
+        auto pct = [](unsigned long long a, unsigned long long b) { return b ? 100.0 * (double)a / (double)b : 0.0; };
+        fprintf(stderr, "[ifb]   producer: waits descriptor ring %.1f %%, stage free %.1f %%;  MMA issuer: waits accumulator free "
+                        "%.1f %%, operands landed %.1f %%;  epilogue warp: waits descriptor %.1f %%, accumulator ready %.1f %%, "
+                        "leaf buffer free %.1f %%, drains %.1f %%, walks %.1f %%\n",
+                pct(h[1], h[3]), pct(h[2], h[3]), pct(h[4], h[6]), pct(h[5], h[6]), pct(h[7], h[12]), pct(h[8], h[12]),
+                pct(h[9], h[12]), pct(h[10], h[12]), pct(h[11], h[12]));
     }
     return IFB_OK;
 }
