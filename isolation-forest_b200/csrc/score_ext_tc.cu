@@ -526,7 +526,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         const int buf = pair;                    // blocks with (it & 1) == pair: accumulator / leaf-value buffer `pair`
         uint32_t it = 0;
         const bool st_on = p.stats != nullptr;   // diagnostic cycle accounts (IFB_TC_STATS), reported by warp 2 of each CTA
-        unsigned long long w_mfull = 0, w_tfull = 0, w_lvempty = 0, c_drain = 0, c_walk = 0;
+        unsigned long long w_mfull = 0, w_tfull = 0, w_lvempty = 0, c_drain = 0, c_walk = 0, c_ldtm = 0;
         const long long t_begin = st_on ? clock64() : 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t row = tile * BM + q * 32 + lane;
@@ -549,7 +549,9 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 for (int cc = pi; cc < nchunks; cc += PW) {   // chunks pi, pi + PW, ...
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cc * 32);
                     uint32_t v[32];
+                    const long long t_ld0 = st_on ? clock64() : 0;
                     tmem_ld32(taddr, v);
+                    if (st_on) c_ldtm += (unsigned long long)(clock64() - t_ld0);
                     // Fast path (2.75 instructions per column): the "left" bit of every accumulator, and ONE chunk-wide
                     // test for ambiguity -- the smallest |dlt| of the 32 columns against the largest bound of the chunk.
                     // Only chunks that fail it (rare at d <= 64) compute the per-column "ambiguous" bits.
@@ -720,6 +722,7 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             atomicAdd(p.stats + 10, c_drain);
             atomicAdd(p.stats + 11, c_walk);
             atomicAdd(p.stats + 12, (unsigned long long)(clock64() - t_begin));
+            atomicAdd(p.stats + 13, c_ldtm);
         }
     }
     tc_fence_before();
@@ -1189,9 +1192,9 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
         auto pct = [](unsigned long long a, unsigned long long b) { return b ? 100.0 * (double)a / (double)b : 0.0; };
         fprintf(stderr, "[ifb]   producer: waits descriptor ring %.1f %%, stage free %.1f %%;  MMA issuer: waits accumulator free "
                         "%.1f %%, operands landed %.1f %%;  epilogue warp: waits descriptor %.1f %%, accumulator ready %.1f %%, "
-                        "leaf buffer free %.1f %%, drains %.1f %%, walks %.1f %%\n",
+                        "leaf buffer free %.1f %%, drains %.1f %% (of which in tcgen05.ld + wait %.1f %%), walks %.1f %%\n",
                 pct(h[1], h[3]), pct(h[2], h[3]), pct(h[4], h[6]), pct(h[5], h[6]), pct(h[7], h[12]), pct(h[8], h[12]),
-                pct(h[9], h[12]), pct(h[10], h[12]), pct(h[11], h[12]));
+                pct(h[9], h[12]), pct(h[10], h[12]), pct(h[13], h[12]), pct(h[11], h[12]));
     }
     return IFB_OK;
 }
