@@ -412,9 +412,10 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
         IFB_CUDA(cudaGetLastError());
         f->ext_w_safe = unsafe == 0;
     }
-    // tensor-core layout (fully-extended forests; a forest that does not qualify simply keeps tc_ok = false)
-    if (f->ext_dense_identity && getenv("IFB_EXT_NO_TC") == nullptr) {
-        rc = build_ext_tc_tables(f, child, hp, leaf, off, depthv);
+    // tensor-core layout (fully-extended forests, and sparse hyperplanes as zero-padded columns; a forest that does not
+    // qualify simply keeps tc_ok = false)
+    if (internal > 0 && getenv("IFB_EXT_NO_TC") == nullptr && (f->ext_dense_identity || getenv("IFB_TC_NO_SPARSE") == nullptr)) {
+        rc = build_ext_tc_tables(f, child, hp, leaf, off, depthv, len);
         if (rc) return rc;
     }
     return IFB_OK;
@@ -644,7 +645,8 @@ ifb_forest::~ifb_forest() {
     cudaFree(d_gchild);
     cudaFree(d_groot);
     cudaFree(d_ext_arena);   // every d_ext_* table is a slice of it
-    cudaFree(d_tc_arena);    // every d_tc_* table is a slice of it
+    cudaFree(d_tc_arena);    // every d_tc_* table is a slice of it ...
+    cudaFree(d_tc_slot_len); // ... except the per-slot term counts of sparse forests
 }
 
 using namespace ifb;

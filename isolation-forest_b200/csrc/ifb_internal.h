@@ -175,6 +175,8 @@ struct ifb_forest {
     int32_t *d_tc_col_slot = nullptr;    // [tc_blocks*256] weight slot of the column's node (-1: padding column)
     double *d_tc_col_off = nullptr;      // [tc_blocks*256] f64 split offset of the column's node
     int32_t *d_tc_flag = nullptr;        // set by the column-preparation kernel when a weight row is not fp16-safe
+    bool tc_sparse = false;              // hyperplanes narrower than the matrix: columns are zero-padded, the exact path
+    int32_t *d_tc_slot_len = nullptr;    // reads the stored terms (d_ext_w / d_ext_idx) with these per-slot counts
     unsigned char *d_tc_arena = nullptr;
 
     int64_t device_bytes = 0;
@@ -237,7 +239,8 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
                           bool accumulate_only, cudaStream_t stream);
 // score_ext_tc.cu: tensor-core path of fully-extended forests; returns -1 when the forest / call does not qualify
 int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const std::vector<int32_t> &hp,
-                        const std::vector<float> &leaf, const std::vector<double> &off, const std::vector<uint8_t> &depth);
+                        const std::vector<float> &leaf, const std::vector<double> &off, const std::vector<uint8_t> &depth,
+                        const std::vector<int32_t> &len);
 int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld, int32_t layout,
                              double *scores, int32_t *depth_sum, float *path_sum, bool accumulate_only,
                              cudaStream_t stream, float *probe_out = nullptr);

@@ -105,7 +105,10 @@ struct Params {
     const uint8_t *rflag;          // [n_rows] 0: ordinary row, 1: all-zero row (never ambiguous), 2: non-finite / out-of-range
                                    //          features (every visit takes the exact path)
     const float *xr;               // [n_rows][kp] row-major f32 copy of the rows (exact path)
-    const float *w;                // d_ext_w [slots][k]
+    const float *w;                // d_ext_w [slots][ks]: the hyperplane weights as stored (exact path)
+    const int32_t *idx;            // d_ext_idx [slots][ks] feature index of every term; nullptr: term i reads feature i
+    const int32_t *slot_len;       // [slots] number of terms of the slot; nullptr: every slot has k terms
+    int32_t ks;                    // row stride of w / idx (the forest's widest hyperplane)
     const double *wabs;            // d_ext_wabs [slots]
     const double *col_off;         // [n_blocks*256]
     int32_t max_depth;
@@ -267,13 +270,14 @@ __device__ __forceinline__ float fmin3_abs(float a, float b, float c) {
 //   tier 2: the exact addends p_i summed per lane (i = lane, lane+32, ...) and by a shuffle tree -- a re-association,
 //           |S2 - S_ref| <= 2 gamma_{k-1} sum|p_i| <= 4 k 2^-53 max|x| sum|w| =: E2;   |S2 - off| > E2  =>  same outcome;
 //   tier 3: the reference's sequential order (every lane redundantly).
-__device__ __forceinline__ bool exact_left(const float *__restrict__ xr, const float *__restrict__ wr, int k, double off,
-                                           double wabs, int lane) {
+// `ix` (nullptr = identity) lists the feature of every term, ascending as the reference stores them (ExtendedUtils.scala:27-34).
+__device__ __forceinline__ bool exact_left(const float *__restrict__ xr, const float *__restrict__ wr,
+                                           const int32_t *__restrict__ ix, int k, double off, double wabs, int lane) {
     double acc = 0.0;
     float mx = 0.f;
     bool bad = false;
     for (int i = lane; i < k; i += 32) {
-        const float xv = __ldg(xr + i), wv = __ldg(wr + i);
+        const float xv = __ldg(xr + (ix ? __ldg(ix + i) : i)), wv = __ldg(wr + i);
         const float a = fabsf(xv);
         bad = bad || !(a <= 3.0e38f);
         mx = fmaxf(mx, a);
@@ -289,7 +293,7 @@ __device__ __forceinline__ bool exact_left(const float *__restrict__ xr, const f
     const double E2 = 4.0 * (double)k * 0x1.0p-53 * ((double)mx * wabs * 1.0000002);
     if (!bad && fabs(acc - off) > E2) return acc < off;
     double sq = 0.0;
-    for (int i = 0; i < k; i++) sq = __dadd_rn(sq, (double)__fmul_rn(__ldg(wr + i), __ldg(xr + i)));
+    for (int i = 0; i < k; i++) sq = __dadd_rn(sq, (double)__fmul_rn(__ldg(wr + i), __ldg(xr + (ix ? __ldg(ix + i) : i))));
     return sq < off;
 }
 
@@ -667,8 +671,10 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                                         const uint2 nx = M->next[col];
                                         const int32_t slot = M->slot[col];
                                         const double off = __ldg(p.col_off + (size_t)b * BN + col);
-                                        const bool left = exact_left(p.xr + (size_t)rowL * p.kp, p.w + (size_t)slot * p.k, p.k,
-                                                                     off, __ldg(p.wabs + slot), lane);
+                                        const bool left = exact_left(p.xr + (size_t)rowL * p.kp, p.w + (size_t)slot * p.ks,
+                                                                     p.idx ? p.idx + (size_t)slot * p.ks : nullptr,
+                                                                     p.slot_len ? __ldg(p.slot_len + slot) : p.k, off,
+                                                                     __ldg(p.wabs + slot), lane);
                                         if (lane == Ls) {
                                             cur[c] = left ? nx.x : nx.y;
                                             stuck &= ~(1u << c);
@@ -735,6 +741,18 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 }
 
 // ---- per-forest column preparation --------------------------------------------------------------------------------------
+// Sparse hyperplanes (extensionLevel < d - 1, or a feature subspace): slot s, terms i < len[s] -> dense row of D weights,
+// zeros elsewhere.  A zero weight contributes exact zeros to every product and partial sum of the tensor-core
+// accumulation, so the filter's bound (derived for D terms) holds a fortiori; the exact path keeps using the stored terms.
+__global__ void ext_tc_densify(const float *__restrict__ w, const int32_t *__restrict__ idx, const int32_t *__restrict__ len,
+                               int64_t n_slots, int ks, int D, float *__restrict__ dense) {
+    const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= n_slots) return;
+    const int n = len[s];
+    for (int i = lane; i < n; i += 32) dense[s * D + idx[s * ks + i]] = w[s * ks + i];
+}
+
 // One warp per accumulator column: power-of-two scaling of the weight row (max |w'| in [0.5, 1)), fp16 hi/lo split,
 // ||w'||_2, the node's offset in its scaled domain and the bound of the filter.
 __global__ void ext_tc_prepare_cols(const float *__restrict__ w, const int32_t *__restrict__ col_slot,
@@ -936,13 +954,18 @@ double tc_bound_constant(int k, int kp) {
 }  // namespace
 
 int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const std::vector<int32_t> &hp,
-                        const std::vector<float> &leaf, const std::vector<double> &off, const std::vector<uint8_t> &depth) {
+                        const std::vector<float> &leaf, const std::vector<double> &off, const std::vector<uint8_t> &depth,
+                        const std::vector<int32_t> &len) {
     using namespace tc;
     const int T = f->num_trees;
-    const int k = f->max_nnz;
+    // Width of the GEMM's K dimension = width of the scored matrix.  Fully-extended forests: the hyperplane width;
+    // sparse ones: the model's feature count (or, for tables that do not carry it, the largest index read + 1).
+    const bool sparse = !f->ext_dense_identity;
+    const int k = sparse ? (f->total_num_features > 0 ? f->total_num_features : f->max_feature_index + 1) : f->max_nnz;
     // k <= 1536: ext_tc_prepare_rows stages 32 rows x (k_pad + 1) floats in shared memory (197 KB at the limit); wider
     // hyperplanes keep the CUDA-core wide kernel
-    if (T == 0 || k < 1 || k > 1536 || !f->ext_w_safe || f->max_depth > 255) return IFB_OK;
+    if (T == 0 || k < 1 || k > 1536 || !f->ext_w_safe || f->max_depth > 255 || f->ext_internal_slots == 0) return IFB_OK;
+    if (sparse && (f->max_feature_index >= k || (size_t)f->ext_internal_slots * (size_t)k * 4 > ((size_t)1 << 30))) return IFB_OK;
     const int kp = (k + BK - 1) / BK * BK;
     // ---- pack whole trees into 128-column halves of 256-column blocks, in tree order ----
     std::vector<BlockMeta> metas;
@@ -1040,13 +1063,41 @@ int build_ext_tc_tables(ifb_forest *f, const std::vector<int32_t> &child, const 
     IFB_CUDA(cudaMemsetAsync(f->d_tc_flag, 0, 4, 0));
     const double ck = tc_bound_constant(k, kp);
     const int warps_per_cta = 8;
+    const float *w_cols = f->d_ext_w;   // [slots][k] rows the columns are prepared from
+    float *dense = nullptr;
+    if (sparse) {
+        // per-slot term counts (exact path) + the zero-filled dense rows (column preparation only, freed below)
+        const int64_t slots = f->ext_internal_slots;
+        std::vector<int32_t> slot_len((size_t)slots, 0);
+        for (size_t g = 0; g < hp.size(); g++)
+            if (hp[g] >= 0) slot_len[(size_t)hp[g]] = len[g];
+        IFB_CUDA(cudaMalloc((void **)&f->d_tc_slot_len, (size_t)slots * 4));
+        f->device_bytes += slots * 4;
+        IFB_CUDA(cudaMemcpyAsync(f->d_tc_slot_len, slot_len.data(), (size_t)slots * 4, cudaMemcpyHostToDevice, 0));
+        IFB_CUDA(cudaMalloc((void **)&dense, (size_t)slots * k * 4));
+        cudaError_t e = cudaMemsetAsync(dense, 0, (size_t)slots * k * 4, 0);
+        if (e == cudaSuccess) {
+            ext_tc_densify<<<(unsigned)((slots + 7) / 8), 256>>>(f->d_ext_w, f->d_ext_idx, f->d_tc_slot_len, slots, f->max_nnz, k,
+                                                                  dense);
+            e = cudaGetLastError();
+            count_launch();
+        }
+        if (e != cudaSuccess) {
+            cudaFree(dense);
+            IFB_CUDA(e);
+        }
+        w_cols = dense;
+    }
     ext_tc_prepare_cols<<<(unsigned)((ncols + warps_per_cta - 1) / warps_per_cta), warps_per_cta * 32>>>(
-        f->d_ext_w, f->d_tc_col_slot, f->d_tc_col_off, (int)ncols, k, kp, ck, reinterpret_cast<__half *>(f->d_tc_wh),
+        w_cols, f->d_tc_col_slot, f->d_tc_col_off, (int)ncols, k, kp, ck, reinterpret_cast<__half *>(f->d_tc_wh),
         reinterpret_cast<__half *>(f->d_tc_wl), f->d_tc_meta, f->d_tc_flag);
-    IFB_CUDA(cudaGetLastError());
+    cudaError_t le = cudaGetLastError();
     count_launch();
     int32_t flag = 0;
-    IFB_CUDA(cudaMemcpy(&flag, f->d_tc_flag, 4, cudaMemcpyDeviceToHost));   // also waits for the uploads above
+    if (le == cudaSuccess) le = cudaMemcpy(&flag, f->d_tc_flag, 4, cudaMemcpyDeviceToHost);   // also waits for the uploads above
+    cudaFree(dense);
+    IFB_CUDA(le);
+    f->tc_sparse = sparse;
     f->tc_k = k;
     f->tc_kp = kp;
     f->tc_blocks = NB;
@@ -1151,6 +1202,9 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
         p.rflag = rflag;
         p.xr = xr;
         p.w = f->d_ext_w;
+        p.idx = f->tc_sparse ? f->d_ext_idx : nullptr;
+        p.slot_len = f->tc_sparse ? f->d_tc_slot_len : nullptr;
+        p.ks = f->max_nnz;
         p.wabs = f->d_ext_wabs;
         p.col_off = f->d_tc_col_off;
         p.max_depth = std::max(f->max_depth, 1);

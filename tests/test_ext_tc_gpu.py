@@ -114,6 +114,35 @@ def test_tc_path_matches_the_oracle(nat, oracle, dev, n, d, T, monkeypatch):
     assert_parity(F.score_device(colmajor_cuda(X[:2048]), want_parts=True), [a[:2048] for a in ref])
 
 
+@pytest.mark.parametrize("n,d,T,ext,nf", [(30_000, 64, 40, 9, None), (5_000, 8, 50, 3, None), (9_000, 200, 12, 20, None),
+                                           (20_000, 32, 30, 0, None), (12_000, 48, 25, 47, 16), (4_000, 1024, 6, 63, None)])
+def test_sparse_hyperplanes_take_the_tensor_core_path(nat, oracle, dev, n, d, T, ext, nf, monkeypatch):
+    """extensionLevel < d - 1 (or a feature subspace, maxFeatures < 1): the stored terms become zero-padded accumulator
+    columns; ambiguous visits are decided on the stored terms in their stored order."""
+    X = synth_mixture(n, d, 7000 + d + ext)
+    kw = {} if nf is None else {"num_features": nf}
+    t = oracle.fit_forest(X[:min(n, 20_000)], T, 256, random_seed=6, ext_level=min(ext, (nf or d) - 1), **kw)
+    F = nat.NativeForest.from_tables(t)
+    assert F.ext_tc_info() == ((d + 31) // 32 * 32, F.ext_tc_info()[1]) and F.ext_tc_info()[1] > 0
+    Xs = X.copy()
+    Xs[5::97, 1] = np.nan          # non-finite features, also in coordinates a hyperplane may not read
+    Xs[7::89, d - 1] = np.inf
+    Xs[11::83, :] = 0.0
+    with np.errstate(all="ignore"):
+        ref = oracle.Forest(t).score(Xs, threads=8, want_parts=True)
+    assert_parity(F.score_device(colmajor_cuda(Xs), want_parts=True), ref)
+    assert_parity(F.score_device(torch.from_numpy(Xs).cuda(), want_parts=True), ref)
+    monkeypatch.setenv("IFB_TC_SCALE", "1e30")      # every visit through the exact path on the stored terms
+    assert_parity(F.score_device(colmajor_cuda(Xs[:2048]), want_parts=True), [a[:2048] for a in ref])
+    monkeypatch.delenv("IFB_TC_SCALE")
+    monkeypatch.setenv("IFB_EXT_NO_TC", "1")        # the CUDA-core kernels agree bit for bit
+    old = [a.cpu().numpy() for a in F.score_device(colmajor_cuda(Xs), want_parts=True)]
+    monkeypatch.delenv("IFB_EXT_NO_TC")
+    new = [a.cpu().numpy() for a in F.score_device(colmajor_cuda(Xs), want_parts=True)]
+    for a, b in zip(old, new):
+        assert np.array_equal(a, b)
+
+
 def test_tc_special_values(nat, oracle, dev):
     n, d = 8192, 64
     X = synth_mixture(n, d, 77)
