@@ -331,8 +331,10 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         for (int b = 0; b < 2; b++) {
             mbar_init(bar_tfull(b), 1);
             mbar_init(bar_tempty(b), EPI_WARPS / 2);    // the eight warps of the pair that owns this accumulator buffer
-            mbar_init(bar_lvfull(b), EPI_WARPS / 2);
-            mbar_init(bar_lvempty(b), 1);               // the summing warp
+            // every LANE arrives on the leaf-buffer barriers, releasing its own shared-memory accesses (no reliance on a
+            // warp-level sync in front of a single arrive: also what compute-sanitizer's racecheck can follow)
+            mbar_init(bar_lvfull(b), EPI_WARPS / 2 * 32);
+            mbar_init(bar_lvempty(b), 32);              // the summing warp
         }
         for (int b = 0; b < META_RING; b++) {
             mbar_init(bar_mfull(b), 1);
@@ -493,11 +495,9 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         ds[j] += (int32_t)ld[t * BM + j * 32];
                     }
                 }
+                mbar_arrive(bar_lvempty(buf));
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(bar_lvempty(buf));
-                    mbar_arrive(bar_mempty(mb));
-                }
+                if (lane == 0) mbar_arrive(bar_mempty(mb));
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -712,11 +712,9 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 }
                 if (st_on) c_walk += (unsigned long long)(clock64() - t_walk0);
                 // leaf values and depths of this warp's trees are in shared memory: hand them to the summing warp
+                mbar_arrive(bar_lvfull(buf));
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(bar_lvfull(buf));
-                    mbar_arrive(bar_mempty(mb));
-                }
+                if (lane == 0) mbar_arrive(bar_mempty(mb));
                 // the pair's mask words may be overwritten (next drain) only when both warps are done walking on them
                 asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * PW) : "memory");
             }

@@ -44,4 +44,25 @@ for (n, d, T, ext) in ((3000, 32, 20, -1), (1500, 128, 30, -1), (700, 900, 6, -1
     thr, frac = nat.quantile_device(s, 0.9)                         # radix select
     lab = nat.predict_device(s, thr)
     print("ok", n, d, T, ext, flush=True)
+# the opt-in rank-word standard kernel (score_std_rank.cu): bulk-copy tiles, a ragged tail, plain-load tiles
+os.environ["IFB_STD_RANK"] = "1"
+for (n, d, T) in ((2600, 32, 20), (1537, 7, 9)):
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    tb = O.fit_forest(X, T, 256, random_seed=3)
+    X[::11, min(1, d - 1)] = np.nan
+    F = nat.NativeForest.from_tables(tb)
+    assert F.std_rank_chunks(d) >= 1
+    ref = O.Forest(tb).score(X, want_parts=True)
+    ps = torch.zeros(n, dtype=torch.float32, device="cuda")
+    F.score_partial_device(cm(X), ps)
+    s = F.score_device(cm(X))
+    buf = torch.zeros(d * (n + 3) + 8, dtype=torch.float32, device="cuda")      # unaligned: plain loads
+    view = buf[1:1 + d * (n + 3)].view(d, n + 3)[:, :n]
+    view.copy_(torch.from_numpy(np.ascontiguousarray(X.T)))
+    s2 = F.score_device(view.t())
+    torch.cuda.synchronize()
+    assert np.array_equal(ps.cpu().numpy(), ref[2]) and np.array_equal(s.cpu().numpy(), s2.cpu().numpy())
+    assert np.max(np.abs(s.cpu().numpy() - ref[0]) / ref[0]) < 1e-12
+    print("rank ok", n, d, T, flush=True)
+del os.environ["IFB_STD_RANK"]
 print("sanitize_run done")
