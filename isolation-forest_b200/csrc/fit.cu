@@ -64,6 +64,7 @@ struct FitDev {
     int32_t stage;               // 0: read X through rows[]; 1: sample staged in shared memory; 2: in `sample`
     float *sample;               // [trees][d][n] staged sample when stage == 2
     int32_t warp_nodes;          // standard builder: subtrees of <= 32 rows are built by warp 0 alone (no block barriers)
+    int32_t dbg;                 // IFB_FIT_DBG: tree 0 prints the cycles of its phases
 };
 
 // ---- java.util.Random ---------------------------------------------------------------------------
@@ -286,6 +287,62 @@ __device__ void jr_skip_nextints_warp(JRandom &r, int F, int lane, const LcgJump
     }
 }
 
+// scala.util.Random.shuffle by a whole warp: the len - 1 draws nextInt(len), nextInt(len - 1), ..., nextInt(2) are
+// evaluated 32 at a time from skip-ahead states into `draws` (a draw consumes one LCG step unless its rejection test
+// fires: then lane 0 redoes the whole shuffle sequentially, probability < len^2 / 2^32), and lane 0 applies the swaps in
+// order.  `r` is meaningful in lane 0 only; jl = lcg_jump_steps(lane + 1), j32 = lcg_jump_steps(32).
+__device__ void scala_shuffle_warp(JRandom &r, int32_t *a, int len, int32_t *draws, int lane, const LcgJump &jl,
+                                   const LcgJump &j32) {
+    const unsigned long long M = (1ULL << 48) - 1;
+    const unsigned long long seed0 = __shfl_sync(0xffffffffu, r.seed, 0);
+    unsigned long long base = seed0, last = seed0;
+    const int F = len - 1;   // number of draws
+    bool rej = false;
+    for (int b = 0; b < F; b += 32) {
+        const int i = b + lane;
+        const unsigned long long st = (jl.mul * base + jl.add) & M;
+        if (i < F) {
+            const int bound = len - i, m = bound - 1;
+            const int u = (int)(long long)(st >> 17);   // next(31)
+            int kk;
+            if ((bound & m) == 0) {
+                kk = (int)(((long long)bound * (long long)u) >> 31);
+            } else {
+                kk = u % bound;
+                rej = rej || ((int)((unsigned)u - (unsigned)kk + (unsigned)m) < 0);
+            }
+            draws[i] = kk;
+        }
+        last = __shfl_sync(0xffffffffu, st, min(F - b, 32) - 1);
+        base = (j32.mul * base + j32.add) & M;
+    }
+    const bool any_rej = __any_sync(0xffffffffu, rej);
+    __syncwarp();
+    if (lane == 0) {
+        if (any_rej) {
+            r.seed = seed0;
+            for (int n = len; n >= 2; n--) {
+                const int kk = jr_next_int(r, n);
+                const int32_t tmp = a[n - 1];
+                a[n - 1] = a[kk];
+                a[kk] = tmp;
+            }
+        } else {
+            int kk = F > 0 ? draws[0] : 0;
+            for (int i = 0; i < F; i++) {
+                const int n = len - i;
+                const int kk_next = (i + 1 < F) ? draws[i + 1] : 0;   // `draws` and `a` never alias: keep the next index in flight
+                const int32_t hi = a[n - 1], lo = a[kk];
+                a[n - 1] = lo;
+                a[kk] = hi;
+                kk = kk_next;
+            }
+            if (F > 0) r.seed = last;
+        }
+    }
+    __syncwarp();
+}
+
 // scala.util.Random.shuffle on an int array: for (n <- len to 2 by -1) swap(n-1, nextInt(n))
 __device__ void scala_shuffle(JRandom &r, int32_t *a, int len) {
     for (int n = len; n >= 2; n--) {
@@ -327,6 +384,7 @@ struct Shared {
     int32_t nnz, slot;
     double offset;
     NodeTask stack[72];
+    unsigned long long jmul[33], jadd[33];   // extended builder: LCG jumps of 0, 2, ..., 64 steps (j nextDouble draws)
 };
 
 // block-wide min/max of feature f over rows perm[start .. start+count)
@@ -411,7 +469,7 @@ __device__ void block_partition(Shared &sh, int32_t *perm, int32_t *perm2, int s
 extern __shared__ __align__(16) unsigned char fit_arena[];
 
 template <bool EXT>
-__global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
+__global__ void __launch_bounds__(BT, EXT ? 2 : 4) fit_kernel(const FitDev p) {
     __shared__ Shared sh;
     const int tl = blockIdx.x;                 // tree index inside the shard
     const int tid = threadIdx.x;
@@ -526,6 +584,12 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
         __syncthreads();
     }
     const SampleView val{p, stage_buf, rows};
+    if (EXT && tid < 33) {
+        const LcgJump jj = lcg_jump_steps(2 * tid);
+        sh.jmul[tid] = jj.mul;
+        sh.jadd[tid] = jj.add;
+    }
+    if (EXT) __syncthreads();
 
     int sp = 1;        // thread 0 only
     int nnodes = 0;    // thread 0 only
@@ -770,18 +834,20 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
             const int nnz = p.k;  // min(extensionLevel + 1, dim)
             if (tid == 0) sh.leaf = (cur.height >= p.height_limit || cur.count <= 1) ? 1 : 0;  // :152-153
             __syncthreads();
+            long long tq0 = p.dbg ? clock64() : 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq5 = 0;
             if (!sh.leaf) {
                 for (int i = tid; i < dim; i += BT) feat_perm[i] = i;
                 __syncthreads();
                 if (tid < 32) {
-                    // :160 shuffle, :168 chosen coordinates (thread 0: Fisher-Yates is sequential by nature), then the
-                    // :169 Gaussians by the whole warp (same values, order and stream position as the sequential loop:
-                    // in the reference the draws of :169 follow the shuffle and interleave with nothing else)
-                    if (tid == 0) {
-                        scala_shuffle(rnd, feat_perm, dim);
-                        for (int i = 0; i < nnz; i++) e_idx[i] = feat_idx[feat_perm[i]];
-                    }
+                    // :160 shuffle (its draws 32 at a time from skip-ahead states, the swaps in order by lane 0), :168
+                    // chosen coordinates, then the :169 Gaussians by the whole warp (same values, order and stream
+                    // position as the sequential loop: in the reference the draws of :169 follow the shuffle and
+                    // interleave with nothing else)
+                    const LcgJump jump_lane = lcg_jump_steps(tid + 1), jump_32 = lcg_jump_steps(32);
+                    scala_shuffle_warp(rnd, feat_perm, dim, avail, tid, jump_lane, jump_32);
+                    for (int i = tid; i < nnz; i += 32) e_idx[i] = feat_idx[feat_perm[i]];
                     __syncwarp();
+                    if (p.dbg) tq1 = clock64();
                     jr_fill_gaussians_warp(rnd, e_raw, nnz, tid);
                     if (tid == 0) {
                         double sq = 0.0;
@@ -809,64 +875,224 @@ __global__ void __launch_bounds__(BT) fit_kernel(const FitDev p) {
                 __syncthreads();
                 continue;
             }
-            // per-coordinate min/max over the node's rows: one warp per coordinate, lanes along rows
-            {
-                const int lane = tid & 31, warp = tid >> 5;
-                for (int kk = warp; kk < nnz; kk += BT / 32) {
+            if (p.dbg) tq2 = clock64();
+            // per-coordinate min/max over the node's rows: one warp per coordinate, lanes along rows; four coordinates
+            // in flight per warp (the staged sample may live in an L2 scratch: one dependent load chain per coordinate
+            // left the warp waiting on latency)
+            if (cur.count <= 32) {
+                // small node: one THREAD per coordinate (no shuffles; every load of a thread is independent)
+                for (int kk = tid; kk < nnz; kk += BT) {
                     const int j = e_idx[kk];
                     float mn = INFINITY, mx = -INFINITY;
-                    for (int i = lane; i < cur.count; i += 32) {
+                    int i = 0;
+                    for (; i + 8 <= cur.count; i += 8) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) v[u] = val(perm[cur.start + i + u], j);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            if (v[u] < mn) mn = v[u];
+                            if (v[u] > mx) mx = v[u];
+                        }
+                    }
+                    for (; i < cur.count; i++) {
                         const float v = val(perm[cur.start + i], j);
                         if (v < mn) mn = v;
                         if (v > mx) mx = v;
                     }
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
-                        if (a < mn) mn = a;
-                        if (b > mx) mx = b;
+                    e_mn[kk] = mn;
+                    e_mx[kk] = mx;
+                }
+            } else {
+                const int lane = tid & 31, warp = tid >> 5;
+                constexpr int NW = BT / 32;
+                for (int k0 = warp; k0 < nnz; k0 += 4 * NW) {
+                    float mn[4], mx[4];
+                    int j[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        mn[u] = INFINITY;
+                        mx[u] = -INFINITY;
+                        j[u] = (k0 + u * NW < nnz) ? e_idx[k0 + u * NW] : e_idx[k0];
                     }
-                    if (lane == 0) {
-                        e_mn[kk] = mn;
-                        e_mx[kk] = mx;
+                    for (int i = lane; i < cur.count; i += 32) {
+                        const int pr = perm[cur.start + i];
+                        float v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) v[u] = val(pr, j[u]);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (v[u] < mn[u]) mn[u] = v[u];
+                            if (v[u] > mx[u]) mx[u] = v[u];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float a = __shfl_xor_sync(0xffffffffu, mn[u], o), b = __shfl_xor_sync(0xffffffffu, mx[u], o);
+                            if (a < mn[u]) mn[u] = a;
+                            if (b > mx[u]) mx[u] = b;
+                        }
+                        if (lane == 0 && k0 + u * NW < nnz) {
+                            e_mn[k0 + u * NW] = mn[u];
+                            e_mx[k0 + u * NW] = mx[u];
+                        }
                     }
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                double off = 0.0;
-                for (int kk = 0; kk < nnz; kk++) {                                        // :201-217
-                    const double mn = (double)e_mn[kk], mx = (double)e_mx[kk];
-                    const double iv = (mn == mx) ? mn : mn + jr_next_double(rnd) * (mx - mn);
-                    off += (double)e_w[kk] * iv;
+            if (p.dbg) tq3 = clock64();
+            if (tid < 32) {
+                // :201-217: p_j = mn if mn == mx else mn + nextDouble() * (mx - mn), in coordinate order.  Which coordinates
+                // draw is known (e_mn / e_mx), so the draws are taken 32 coordinates at a time from skip-ahead states
+                // (nextDouble = two LCG steps, no rejection); the f64 sum of w_j * p_j stays sequential on lane 0.
+                const unsigned long long M48 = (1ULL << 48) - 1;
+                unsigned long long base = __shfl_sync(0xffffffffu, rnd.seed, 0);
+                for (int b = 0; b < nnz; b += 32) {
+                    const int kk = b + tid;
+                    const bool in = kk < nnz;
+                    const double mn = in ? (double)e_mn[kk] : 0.0, mx = in ? (double)e_mx[kk] : 0.0;
+                    const bool draws = in && !(mn == mx);
+                    const unsigned dm = __ballot_sync(0xffffffffu, draws);
+                    const int before = __popc(dm & ((1u << tid) - 1u));
+                    double iv = mn;
+                    if (draws) {
+                        JRandom t;
+                        t.seed = (sh.jmul[before] * base + sh.jadd[before]) & M48;
+                        t.have_next = 0;
+                        t.next_gauss = 0.0;
+                        iv = mn + jr_next_double(t) * (mx - mn);
+                    }
+                    if (in) e_raw[kk] = iv;   // the raw Gaussians are no longer needed
+                    const int nd = __popc(dm);
+                    base = (sh.jmul[nd] * base + sh.jadd[nd]) & M48;
                 }
-                sh.offset = off;
-                sh.slot = ninternal++;
-                o_left[id] = id + 1;
-                o_off[id] = off;
-                o_slot[id] = sh.slot;
-                o_ninst[id] = -1;
+                __syncwarp();
+                if (tid == 0) {
+                    rnd.seed = base;
+                    double off = 0.0;
+                    int kk = 0;
+                    for (; kk + 8 <= nnz; kk += 8) {   // operands first, then the f64 sum in coordinate order
+                        double pw[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) pw[u] = (double)e_w[kk + u] * e_raw[kk + u];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) off += pw[u];
+                    }
+                    for (; kk < nnz; kk++) off += (double)e_w[kk] * e_raw[kk];
+                    sh.offset = off;
+                    sh.slot = ninternal++;
+                    o_left[id] = id + 1;
+                    o_off[id] = off;
+                    o_slot[id] = sh.slot;
+                    o_ninst[id] = -1;
+                }
             }
             __syncthreads();
-            // canonical order (:220-226): rank of each chosen index among the chosen indices
+            if (p.dbg) tq4 = clock64();
+            // canonical order (:220-226): rank of each chosen index among the chosen indices.  e_idx[i] =
+            // feat_idx[feat_perm[i]] with feat_idx ascending, so when every coordinate is chosen the rank is feat_perm[i].
+            // The ordered copy also goes to shared memory (e_mn / e_mx are free now) for the partition's dot products.
             int32_t *h_idx = p.hp_idx + ((int64_t)tl * p.cap_internal + sh.slot) * p.k;
             float *h_w = p.hp_w + ((int64_t)tl * p.cap_internal + sh.slot) * p.k;
+            float *s_w = e_mn;
+            int32_t *s_idx = reinterpret_cast<int32_t *>(e_mx);
             for (int i = tid; i < nnz; i += BT) {
                 const int32_t me = e_idx[i];
                 int rank = 0;
-                for (int q = 0; q < nnz; q++) rank += (e_idx[q] < me) ? 1 : 0;
+                if (nnz == dim) {
+                    rank = feat_perm[i];
+                } else {
+                    for (int q = 0; q < nnz; q++) rank += (e_idx[q] < me) ? 1 : 0;
+                }
+                const float wv = e_w[i];
                 h_idx[rank] = me;
-                h_w[rank] = e_w[i];
+                h_w[rank] = wv;
+                s_idx[rank] = me;
+                s_w[rank] = wv;
             }
             __syncthreads();
             const double off = sh.offset;
-            block_partition(sh, perm, perm2, cur.start, cur.count, [&](int32_t pr) {      // :230-232
-                double sum = 0.0;
-                for (int q = 0; q < nnz; q++) {
-                    const float prod = __fmul_rn(h_w[q], val(pr, h_idx[q]));
-                    sum = sum + (double)prod;
+            // :230-232  left iff dot(x) < offset with the reference's arithmetic (f32 products, f64 sum in index order).
+            // One WARP per row: every lane sums the exact addends of its 1/32 of the terms, a butterfly adds the partial
+            // sums -- a re-association whose distance from the sequential sum is <= 4 k 2^-53 max|x| sum|w| (the same
+            // bound, with the same proof, as tier 2 of the scoring kernels) -- and only rows closer to
+            // the offset than that, or with non-finite features, redo the sum sequentially.  All the loads of a row are
+            // in flight at once; a thread per row walked 1024 dependent terms with the staged sample in L2.
+            uint8_t *go_left_flag = reinterpret_cast<uint8_t *>(e_raw);    // [n] by sample slot; e_raw (8 k bytes) is free by now
+            // (wide hyperplanes and small nodes only: with few terms, or all 256 threads busy, a thread per row is faster)
+            const bool warp_rows = nnz >= 256 && p.n <= 8 * p.k && cur.count <= 64;
+            if (warp_rows) {
+                const int lane = tid & 31, warp = tid >> 5;
+                double wabs = 0.0;
+                for (int q = lane; q < nnz; q += 32) wabs += fabs((double)s_w[q]);
+                for (int o = 16; o > 0; o >>= 1) wabs += __shfl_xor_sync(0xffffffffu, wabs, o);
+                wabs *= 1.0000001;   // lane-parallel sum instead of a sequential one: <= k 2^-53 relative
+                for (int i = warp; i < cur.count; i += BT / 32) {
+                    const int pr = perm[cur.start + i];
+                    double acc = 0.0;
+                    float mxa = 0.f;
+                    bool bad = false;
+                    for (int q0 = lane; q0 < nnz; q0 += 32 * 8) {
+                        float v[8], w8[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int q = q0 + 32 * u;
+                            v[u] = q < nnz ? val(pr, s_idx[q]) : 0.f;
+                            w8[u] = q < nnz ? s_w[q] : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const float a = fabsf(v[u]);
+                            bad = bad || !(a <= 3.0e38f);
+                            mxa = fmaxf(mxa, a);
+                            acc = acc + (double)__fmul_rn(w8[u], v[u]);
+                        }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        acc = acc + __shfl_xor_sync(0xffffffffu, acc, o);
+                        mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, o));
+                    }
+                    bad = __any_sync(0xffffffffu, bad);
+                    const double E2 = 4.0 * (double)nnz * 0x1.0p-53 * ((double)mxa * wabs * 1.0000002);
+                    bool left;
+                    if (!bad && fabs(acc - off) > E2) {
+                        left = acc < off;
+                    } else {   // every lane redundantly: the reference's own order
+                        double sq = 0.0;
+                        for (int q = 0; q < nnz; q++) sq = sq + (double)__fmul_rn(s_w[q], val(pr, s_idx[q]));
+                        left = sq < off;
+                    }
+                    if (lane == 0) go_left_flag[pr] = left ? 1 : 0;
                 }
+                __syncthreads();
+            }
+            block_partition(sh, perm, perm2, cur.start, cur.count, [&](int32_t pr) {
+                if (warp_rows) return go_left_flag[pr] != 0;
+                double sum = 0.0;
+                int q = 0;
+                for (; q + 32 <= nnz; q += 32) {    // 32 loads in flight (the staged sample may sit in L2), the f64 sum in
+                    float v[32];                    // index order
+#pragma unroll
+                    for (int u = 0; u < 32; u++) v[u] = val(pr, s_idx[q + u]);
+#pragma unroll
+                    for (int u = 0; u < 32; u++) sum = sum + (double)__fmul_rn(s_w[q + u], v[u]);
+                }
+                for (; q + 8 <= nnz; q += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v[u] = val(pr, s_idx[q + u]);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) sum = sum + (double)__fmul_rn(s_w[q + u], v[u]);
+                }
+                for (; q < nnz; q++) sum = sum + (double)__fmul_rn(s_w[q], val(pr, s_idx[q]));
                 return sum < off;
             });
+            if (p.dbg && tl == 0 && tid == 0) {
+                tq5 = clock64();
+                printf("[ifb fit dbg] node %d count %d: shuffle %lld gauss+norm %lld minmax %lld offsets %lld rank+partition %lld cycles\n",
+                       id, cur.count, tq1 - tq0, tq2 - tq1, tq3 - tq2, tq4 - tq3, tq5 - tq4);
+            }
             if (tid == 0) {
                 const int nl = sh.nl;
                 sh.stack[sp++] = NodeTask{cur.start + nl, cur.count - nl, cur.height + 1, id, 1};
@@ -1040,6 +1266,7 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     p.small_in_smem = small_bytes <= kSmallMax && !no_stage;
     p.stage = 0;
     p.warp_nodes = std::getenv("IFB_FIT_NO_WARP_NODES") == nullptr ? 1 : 0;   // A/B hook: 0 = every node through the block path
+    p.dbg = std::getenv("IFB_FIT_DBG") != nullptr ? 1 : 0;      // tree 0 prints the cycles of its phases (device printf)
     DevBuf b_sample(stream);
     if (!no_stage) {
         if (p.small_in_smem && small_aligned + sample_bytes <= kArenaMax) p.stage = 1;
