@@ -15,8 +15,6 @@ int launch_transpose(const float *in, int64_t n, int32_t d, int64_t ld_in, float
 int launch_select(const double *scores, int64_t n, int64_t rank0, double *value, unsigned long long *count_ge,
                   cudaStream_t stream);
 
-namespace {
-
 // keep stream-ordered allocations cached instead of returning them to the OS after every call
 void tune_mempool(int device) {
     static std::mutex mu;
@@ -30,6 +28,8 @@ void tune_mempool(int device) {
     }
     done.push_back(device);
 }
+
+namespace {
 
 // The require()s at the top of transform (IF/IsolationForestModel.scala:118-125,
 // IF/extended/ExtendedIsolationForestModel.scala:100-107) and the per-row dimension check

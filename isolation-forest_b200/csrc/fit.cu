@@ -1226,35 +1226,52 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     p.k = k; p.tree_begin = tb; p.height_limit = hl; p.cap = (int32_t)cap; p.cap_internal = (int32_t)cap_internal;
     p.hcap = hcap;
 
-    DevBuf b_nn(stream), b_ni(stream), b_left(stream), b_right(stream), b_ninst(stream), b_feat(stream), b_thr(stream),
-        b_off(stream), b_slot(stream), b_hidx(stream), b_hw(stream), b_rows(stream), b_perm(stream), b_perm2(stream),
-        b_hk(stream), b_hv(stream), b_fperm(stream), b_fidx(stream), b_avail(stream), b_eidx(stream), b_eraw(stream),
-        b_ew(stream), b_emn(stream), b_emx(stream);
+    // every output / scratch array of the launch is a 256-byte aligned slice of ONE stream-ordered allocation (two
+    // dozen pool allocations per call were a tenth of a small fit)
+    DevBuf b_arena(stream);
     int rc;
     const size_t T = (size_t)std::max(ntrees, 1);
-#define ALLOC(buf, bytes)                     \
-    if ((rc = (buf).alloc(bytes))) return rc;
-    ALLOC(b_nn, T * 4) ALLOC(b_ni, T * 4) ALLOC(b_left, T * cap * 4) ALLOC(b_right, T * cap * 4)
-    ALLOC(b_ninst, T * cap * 8) ALLOC(b_rows, T * n * 8) ALLOC(b_perm, T * n * 4) ALLOC(b_perm2, T * n * 4)
-    ALLOC(b_hk, T * hcap * 8) ALLOC(b_hv, T * hcap * 8) ALLOC(b_fperm, T * d * 4)
-    ALLOC(b_fidx, T * prm->num_features * 4) ALLOC(b_avail, T * prm->num_features * 4)
+    struct Slice {
+        void **dst;
+        size_t bytes, at;
+    };
+    std::vector<Slice> slices;
+    size_t arena_bytes = 0;
+    auto take = [&](void **dst, size_t bytes) {
+        slices.push_back(Slice{dst, bytes, arena_bytes});
+        arena_bytes += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+    };
+    take((void **)&p.n_nodes, T * 4);
+    take((void **)&p.n_internal, T * 4);
+    take((void **)&p.left, T * cap * 4);
+    take((void **)&p.right, T * cap * 4);
+    take((void **)&p.num_instances, T * cap * 8);
+    take((void **)&p.rows, T * n * 8);
+    take((void **)&p.perm, T * n * 4);
+    take((void **)&p.perm2, T * n * 4);
+    take((void **)&p.hkeys, T * hcap * 8);
+    take((void **)&p.hvals, T * hcap * 8);
+    take((void **)&p.feat_perm, T * d * 4);
+    take((void **)&p.feat_idx, T * prm->num_features * 4);
+    take((void **)&p.avail, T * prm->num_features * 4);
+    p.feature = nullptr; p.threshold = nullptr; p.offset = nullptr; p.hp_slot = nullptr; p.hp_idx = nullptr; p.hp_w = nullptr;
+    p.e_idx = nullptr; p.e_raw = nullptr; p.e_w = nullptr; p.e_mn = nullptr; p.e_mx = nullptr;
     if (ext) {
-        ALLOC(b_off, T * cap * 8) ALLOC(b_slot, T * cap * 4) ALLOC(b_hidx, T * cap_internal * k * 4)
-        ALLOC(b_hw, T * cap_internal * k * 4) ALLOC(b_eidx, T * k * 4) ALLOC(b_eraw, T * k * 8) ALLOC(b_ew, T * k * 4)
-        ALLOC(b_emn, T * k * 4) ALLOC(b_emx, T * k * 4)
+        take((void **)&p.offset, T * cap * 8);
+        take((void **)&p.hp_slot, T * cap * 4);
+        take((void **)&p.hp_idx, T * cap_internal * k * 4);
+        take((void **)&p.hp_w, T * cap_internal * k * 4);
+        take((void **)&p.e_idx, T * k * 4);
+        take((void **)&p.e_raw, T * k * 8);
+        take((void **)&p.e_w, T * k * 4);
+        take((void **)&p.e_mn, T * k * 4);
+        take((void **)&p.e_mx, T * k * 4);
     } else {
-        ALLOC(b_feat, T * cap * 4) ALLOC(b_thr, T * cap * 8)
+        take((void **)&p.feature, T * cap * 4);
+        take((void **)&p.threshold, T * cap * 8);
     }
-#undef ALLOC
-    p.n_nodes = b_nn.as<int32_t>(); p.n_internal = b_ni.as<int32_t>();
-    p.left = b_left.as<int32_t>(); p.right = b_right.as<int32_t>(); p.num_instances = b_ninst.as<int64_t>();
-    p.feature = b_feat.as<int32_t>(); p.threshold = b_thr.as<double>();
-    p.offset = b_off.as<double>(); p.hp_slot = b_slot.as<int32_t>(); p.hp_idx = b_hidx.as<int32_t>(); p.hp_w = b_hw.as<float>();
-    p.rows = b_rows.as<int64_t>(); p.perm = b_perm.as<int32_t>(); p.perm2 = b_perm2.as<int32_t>();
-    p.hkeys = b_hk.as<int64_t>(); p.hvals = b_hv.as<int64_t>();
-    p.feat_perm = b_fperm.as<int32_t>(); p.feat_idx = b_fidx.as<int32_t>(); p.avail = b_avail.as<int32_t>();
-    p.e_idx = b_eidx.as<int32_t>(); p.e_raw = b_eraw.as<double>(); p.e_w = b_ew.as<float>();
-    p.e_mn = b_emn.as<float>(); p.e_mx = b_emx.as<float>();
+    if ((rc = b_arena.alloc(arena_bytes))) return rc;
+    for (const Slice &sl : slices) *sl.dst = b_arena.as<unsigned char>() + sl.at;
 
     // shared-memory arena (must mirror the carve-up at the top of fit_kernel)
     const size_t small_bytes = (size_t)hcap * 16 + (ext ? (size_t)k * 8 : 0) +

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <queue>
 
@@ -28,7 +29,7 @@ static std::atomic_llong g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // Utils.avgPathLength, IF/core/Utils.scala:85-92: f32 arithmetic around an f64 log rounded to f32.
-float avg_path_length_host(int64_t n) {
+static float avg_path_length_compute(int64_t n) {
     if (n <= 1) return 0.0f;
     const float euler = 0.5772156649f;
     volatile float nf = (float)n;
@@ -36,6 +37,18 @@ float avg_path_length_host(int64_t n) {
     volatile float a = 2.0f * (lg + euler);
     volatile float b = (2.0f * (nf - 1.0f)) / nf;
     return a - b;
+}
+// Leaf sizes are bounded by maxSamples, so the same few hundred values are asked for once per leaf of every forest:
+// a table for n < 4096 (filled once) takes the log() out of forest creation.
+float avg_path_length_host(int64_t n) {
+    constexpr int kTable = 4096;
+    static std::once_flag once;
+    static float table[kTable];
+    if (n < 0 || n >= kTable) return avg_path_length_compute(n);
+    std::call_once(once, [] {
+        for (int i = 0; i < kTable; i++) table[i] = avg_path_length_compute(i);
+    });
+    return table[n];
 }
 
 int device_smem_optin(int device) {
@@ -559,13 +572,23 @@ int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out) {
     }
     p->total_words = (int64_t)val.size();
     DeviceGuard dg(f->device);
-    IFB_CUDA(cudaMalloc((void **)&p->d_val, std::max<size_t>(16, val.size() * 4)));
-    IFB_CUDA(cudaMalloc((void **)&p->d_meta, std::max<size_t>(16, meta.size() * 4)));
-    IFB_CUDA(cudaMalloc((void **)&p->d_tree_root, std::max<size_t>(16, roots.size() * 4)));
-    IFB_CUDA(cudaMemcpy(p->d_val, val.data(), val.size() * 4, cudaMemcpyHostToDevice));
-    IFB_CUDA(cudaMemcpy(p->d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
-    IFB_CUDA(cudaMemcpy(p->d_tree_root, roots.data(), roots.size() * 4, cudaMemcpyHostToDevice));
-    f->device_bytes += (int64_t)(val.size() * 8 + roots.size() * 4);
+    // one allocation and one copy for the three tables (a cudaMalloc + blocking cudaMemcpy each was a quarter of
+    // BASELINE config 1's fit + transform): [ val | meta | roots ], every part 256-byte aligned
+    {
+        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_val = al(val.size() * 4), b_meta = al(meta.size() * 4), b_root = al(roots.size() * 4);
+        std::vector<unsigned char> pack(b_val + b_meta + b_root, 0);
+        std::memcpy(pack.data(), val.data(), val.size() * 4);
+        std::memcpy(pack.data() + b_val, meta.data(), meta.size() * 4);
+        std::memcpy(pack.data() + b_val + b_meta, roots.data(), roots.size() * 4);
+        unsigned char *base = nullptr;
+        IFB_CUDA(cudaMalloc((void **)&base, std::max<size_t>(256, pack.size())));
+        p->d_val = reinterpret_cast<float *>(base);
+        p->d_meta = reinterpret_cast<uint32_t *>(base + b_val);
+        p->d_tree_root = reinterpret_cast<uint32_t *>(base + b_val + b_meta);
+        IFB_CUDA(cudaMemcpy(base, pack.data(), pack.size(), cudaMemcpyHostToDevice));
+        f->device_bytes += (int64_t)pack.size();
+    }
     f->std_plans.push_back(p);
     *out = p;
     return IFB_OK;
@@ -634,9 +657,7 @@ int create_extended_from_device(int32_t device, int32_t num_trees, const int32_t
 ifb_forest::~ifb_forest() {
     ifb::DeviceGuard dg(device);
     for (auto *p : std_plans) {
-        cudaFree(p->d_val);
-        cudaFree(p->d_meta);
-        cudaFree(p->d_tree_root);
+        cudaFree(p->d_val);   // d_meta and d_tree_root are slices of the same allocation
         delete p;
     }
     ifb::free_rank_plans(this);
@@ -683,15 +704,25 @@ int ifb_host_free(void *ptr) {
     if (ptr) IFB_CUDA(cudaFreeHost(ptr));
     return IFB_OK;
 }
+// Served from the device's stream-ordered pool (the legacy default stream; the pool keeps freed blocks, see
+// tune_mempool): a cudaMalloc / cudaFree pair synchronises the whole device and cost a quarter of a small fit.  The
+// allocation is synchronised before it is handed out, the free waits for the legacy stream (which, by CUDA's rules, has
+// waited for every blocking stream); work queued on NON-blocking streams must be complete before a buffer is freed --
+// the contract cudaFree users already follow in practice.
 int ifb_device_alloc(int32_t device, size_t bytes, void **ptr) {
     IFB_REQUIRE(ptr, "ptr is null");
     DeviceGuard dg(device);
-    IFB_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+    tune_mempool(device);
+    IFB_CUDA(cudaMallocAsync(ptr, bytes ? bytes : 1, 0));
+    IFB_CUDA(cudaStreamSynchronize(0));
     return IFB_OK;
 }
 int ifb_device_free(int32_t device, void *ptr) {
     DeviceGuard dg(device);
-    if (ptr) IFB_CUDA(cudaFree(ptr));
+    if (ptr) {
+        IFB_CUDA(cudaStreamSynchronize(0));
+        IFB_CUDA(cudaFreeAsync(ptr, 0));
+    }
     return IFB_OK;
 }
 
@@ -742,8 +773,16 @@ int ifb_forest_create_standard(int32_t device, int32_t num_trees, const int32_t 
     IFB_REQUIRE(total_num_features == -1 || total_num_features > 0,
                 "parameter totalNumFeatures must be >0 or UnknownTotalNumFeatures, but given invalid value %d",
                 total_num_features);
+    const bool timing = getenv("IFB_FIT_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (timing)
+            std::fprintf(stderr, "[ifb create] %s at %.3f ms\n", what,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
     rc = validate_shape(num_trees, node_off, left, right, num_instances, /*allow_empty_leaf=*/false);
     if (rc) return rc;
+    lap("shape validated");
     const int64_t total = node_off[num_trees];
     IFB_REQUIRE(total == 0 || (feature && threshold), "null split table");
     for (int64_t g = 0; g < total; g++) {
@@ -769,11 +808,13 @@ int ifb_forest_create_standard(int32_t device, int32_t num_trees, const int32_t 
     f->feature.assign(feature, feature + total);
     f->threshold.assign(threshold, threshold + total);
     f->num_instances.assign(num_instances, num_instances + total);
+    lap("tables copied");
     rc = build_standard_tables(f);
     if (rc) {
         delete f;
         return rc;
     }
+    lap("kernel layout built");
     *out = f;
     return IFB_OK;
 }

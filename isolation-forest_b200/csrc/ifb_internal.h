@@ -36,6 +36,7 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 void count_launch(int n = 1);
+void tune_mempool(int device);   // api.cu: the device's stream-ordered pool keeps freed blocks
 
 // RAII device guard
 struct DeviceGuard {
