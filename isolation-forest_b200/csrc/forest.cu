@@ -205,6 +205,13 @@ __global__ void ext_patch_wide_nodes_kernel(WideNode *nodes, int64_t n_nodes, co
 }  // namespace
 
 int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
+    const bool timing = getenv("IFB_FIT_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (timing)
+            std::fprintf(stderr, "[ifb ext tables] %s at %.3f ms\n", what,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
     const int T = f->num_trees;
     const int64_t total = f->node_off[T];
     const int k = f->max_nnz;
@@ -263,6 +270,7 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
         }
     }
     f->ext_internal_slots = internal;
+    lap("BFS relayout, weights / indices");
     f->ext_dense_identity = identity && internal > 0;
     DeviceGuard dg(f->device);
     // Every table goes into ONE device allocation (a dozen cudaMallocs cost more than the uploads): `up` records
@@ -352,6 +360,7 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
             if (!(std::fabs(wv) <= 0x1p40f)) wsafe = false;
         f->ext_w_safe = wsafe;
     }
+    lap("bounds, wide-node records");
     // ---- per-tree blobs for the dense kernel ----
     if (f->ext_dense_identity && k <= 64) {
         const int D = k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64;
@@ -404,7 +413,9 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
         if ((rc = up((void **)&f->d_ext_blob, blob.data(), blob.size()))) return rc;
         if ((rc = up((void **)&f->d_ext_blob_off, boff.data(), boff.size() * 8))) return rc;
     }
+    lap("dense-kernel blobs");
     rc = commit();
+    lap("arena allocated, uploads queued");
     if (rc) return rc;
     if (dev && internal > 0) {
         int64_t *d_src = nullptr;
@@ -430,6 +441,7 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
     if (internal > 0 && getenv("IFB_EXT_NO_TC") == nullptr && (f->ext_dense_identity || getenv("IFB_TC_NO_SPARSE") == nullptr)) {
         rc = build_ext_tc_tables(f, child, hp, leaf, off, depthv, len);
         if (rc) return rc;
+        lap("tensor-core tables");
     }
     return IFB_OK;
 }
