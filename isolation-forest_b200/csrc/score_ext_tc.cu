@@ -47,13 +47,9 @@ namespace tc {
 
 constexpr int BM = 128;        // rows per tile (TMEM lanes)
 constexpr int BN = 256;        // hyperplanes (accumulator columns) per block
-constexpr int BK = 32;         // K chunk in elements (64 bytes of fp16: one 64B swizzle atom row)
-constexpr int STAGES = 3;
+constexpr int BK = 32;         // padding unit of K (the widest K chunk per stage, see Geo)
 constexpr int MAX_TREES_PER_BLOCK = 16;
 constexpr int MAX_LEAVES_PER_BLOCK = 256;   // node ids stay below 512: bit 8 alone tells a leaf from an internal node
-constexpr uint32_t A_BYTES = BM * BK * 2;   //  8 KB
-constexpr uint32_t B_BYTES = BN * BK * 2;   // 16 KB
-constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl: 48 KB
 #ifndef IFB_TC_PW
 #define IFB_TC_PW 2
 #endif
@@ -84,16 +80,30 @@ struct BlockMeta {
 static_assert(sizeof(BlockMeta) % 16 == 0, "bulk copies need 16-byte multiples");
 constexpr uint32_t META_BYTES = sizeof(BlockMeta);
 
-// shared-memory carve-up (offsets from a 1024-aligned base)
-constexpr uint32_t OFF_STAGES = 0;
-constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;          // [2 pairs][4 quarters]: {left, ambiguous} words [8][32]
-constexpr uint32_t OFF_LV = OFF_MASKS + 8 * 2048;                          // [2][MAX_TREES_PER_BLOCK][128] leaf values
-constexpr uint32_t OFF_LD = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;     // [2][MAX_TREES_PER_BLOCK][128] leaf depths (u8)
-constexpr uint32_t OFF_META = OFF_LD + 2 * MAX_TREES_PER_BLOCK * BM;
-constexpr uint32_t OFF_BARS = (OFF_META + META_RING * META_BYTES + 15u) & ~15u;
-constexpr int NBARS = 2 * STAGES + 4 + 2 * META_RING + 4;
-constexpr uint32_t OFF_TMEMPTR = OFF_BARS + NBARS * 8;
-constexpr uint32_t SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;   // + alignment slack
+// Operand stage geometry and shared-memory carve-up (offsets from a 1024-aligned base) for a K chunk of BKT elements per
+// stage.  BKT = 32: 64-byte rows (64B swizzle), two k-steps per stage, 3 stages of 48 KB.  BKT = 16: 32-byte rows (32B
+// swizzle), one k-step per stage, 6 stages of 24 KB -- the same bytes, but five stages instead of two in flight while one
+// is consumed: wide hyperplanes are bound by the latency of the operand feed (the MMA issuer waited for operands 31 % of
+// the time with 3 x 48 KB, profiles/r02_score_ext_tc_v10_ncu.md).
+template <int BKT>
+struct Geo {
+    static_assert(BKT == 16 || BKT == 32, "K chunk of one or two 16-wide k-steps");
+    static constexpr int BK = BKT;
+    static constexpr int STAGES = BKT == 32 ? 3 : 6;
+    static constexpr uint32_t A_BYTES = BM * BKT * 2;
+    static constexpr uint32_t B_BYTES = BN * BKT * 2;
+    static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl
+    static constexpr uint32_t OFF_STAGES = 0;
+    static constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;   // [2 teams][4 quarters]: {left, ambiguous} words [8][32]
+    static constexpr uint32_t OFF_LV = OFF_MASKS + 8 * 2048;                   // [2][MAX_TREES_PER_BLOCK][128] leaf values
+    static constexpr uint32_t OFF_LD = OFF_LV + 2 * MAX_TREES_PER_BLOCK * BM * 4;   // [2][MAX_TREES_PER_BLOCK][128] leaf depths (u8)
+    static constexpr uint32_t OFF_META = OFF_LD + 2 * MAX_TREES_PER_BLOCK * BM;
+    static constexpr uint32_t OFF_BARS = (OFF_META + META_RING * META_BYTES + 15u) & ~15u;
+    static constexpr int NBARS = 2 * STAGES + 4 + 2 * META_RING + 4;
+    static constexpr uint32_t OFF_TMEMPTR = OFF_BARS + NBARS * 8;
+    static constexpr uint32_t SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;   // + alignment slack
+    static_assert(SMEM_BYTES <= 232448, "stage ring does not fit the 227 KB of an sm_100 CTA");
+};
 
 struct Params {
     const unsigned char *meta;     // [n_blocks] BlockMeta
@@ -239,6 +249,10 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
+// the same with 32-byte rows: 8-row groups 256 bytes apart, layout type 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(256u >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format = F32 (bits 4-5 = 1), a/b format F16 (0), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24
 __device__ __forceinline__ constexpr uint32_t umma_idesc_f16(int M, int N) {
@@ -302,10 +316,15 @@ __device__ __forceinline__ bool exact_left(const float *__restrict__ xr, const f
 // B tile from L2 ONCE: CTA r loads rows [r*256/CL, (r+1)*256/CL) of wh / wl and TMA-multicasts them into the same stage
 // of all CL CTAs (the operand feed, not the MMA, bounds this kernel: 48 KB per stage per SM from L2 without sharing).
 // A stage may be refilled once the MMAs of ALL CL CTAs have read it: tcgen05.commit arrives on every CTA's empty barrier.
-template <bool HOOK, int CL>
+template <bool HOOK, int CL, int BKT>
 __global__ void __launch_bounds__(THREADS, 1)
 score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                     const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, const Params p) {
+    using G = Geo<BKT>;
+    constexpr int BK = G::BK, STAGES = G::STAGES;
+    constexpr uint32_t A_BYTES = G::A_BYTES, B_BYTES = G::B_BYTES, STAGE_BYTES = G::STAGE_BYTES, OFF_STAGES = G::OFF_STAGES,
+                       OFF_MASKS = G::OFF_MASKS, OFF_LV = G::OFF_LV, OFF_LD = G::OFF_LD, OFF_META = G::OFF_META,
+                       OFF_BARS = G::OFF_BARS, OFF_TMEMPTR = G::OFF_TMEMPTR;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (s32(smem_raw) + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (base - s32(smem_raw));
@@ -423,10 +442,11 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                         const uint32_t st = base + OFF_STAGES + (uint32_t)stage * STAGE_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ks++) {
-                            const uint64_t a_h = umma_desc_sw64(st + ks * 32);
-                            const uint64_t a_l = umma_desc_sw64(st + A_BYTES + ks * 32);
-                            const uint64_t b_h = umma_desc_sw64(st + 2 * A_BYTES + ks * 32);
-                            const uint64_t b_l = umma_desc_sw64(st + 2 * A_BYTES + B_BYTES + ks * 32);
+                            auto desc = [](uint32_t a) { return BKT == 32 ? umma_desc_sw64(a) : umma_desc_sw32(a); };
+                            const uint64_t a_h = desc(st + ks * 32);
+                            const uint64_t a_l = desc(st + A_BYTES + ks * 32);
+                            const uint64_t b_h = desc(st + 2 * A_BYTES + ks * 32);
+                            const uint64_t b_l = desc(st + 2 * A_BYTES + B_BYTES + ks * 32);
                             umma_f16(d_tmem, a_h, b_h, idesc, (kc | ks) != 0 ? 1u : 0u);
                             umma_f16(d_tmem, a_l, b_h, idesc, 1u);
                             umma_f16(d_tmem, a_h, b_l, idesc, 1u);
@@ -910,8 +930,8 @@ EncodeTiledFn tc_encode_fn() {
     return fn;
 }
 
-// fp16 matrix [rows][kp] (K contiguous) -> tensor map with a (32 x box_rows) box and the 64-byte swizzle UMMA expects
-int make_tc_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int32_t kp, int box_rows) {
+// fp16 matrix [rows][kp] (K contiguous) -> tensor map with a (bk x box_rows) box and the swizzle (64B / 32B rows) UMMA expects
+int make_tc_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int32_t kp, int box_rows, int bk) {
     EncodeTiledFn enc = tc_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -919,13 +939,14 @@ int make_tc_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int32_t kp, in
     }
     cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)kp * 2};
-    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled (fp16 %lld x %d, box %d x %d) failed with CUresult %d", (long long)rows, kp, tc::BK,
+        set_error("cuTensorMapEncodeTiled (fp16 %lld x %d, box %d x %d) failed with CUresult %d", (long long)rows, kp, bk,
                   box_rows, (int)r);
         return IFB_ECUDA;
     }
@@ -1143,10 +1164,14 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     // pack the 148 SMs exactly.
     const int cl_env = getenv("IFB_TC_CLUSTER") ? atoi(getenv("IFB_TC_CLUSTER")) : (kp >= 256 ? 4 : 2);
     const int CL = (cl_env == 1 || cl_env == 4) ? cl_env : 2;
+    // K chunk per operand stage (IFB_TC_BK = 16 | 32 overrides): wide hyperplanes take 6 fine stages, see Geo
+    const int bk_env = getenv("IFB_TC_BK") ? atoi(getenv("IFB_TC_BK")) : (kp >= 256 ? 16 : 32);
+    const int bk = bk_env == 16 ? 16 : 32;
+    const uint32_t smem_bytes = bk == 16 ? Geo<16>::SMEM_BYTES : Geo<32>::SMEM_BYTES;
     CUtensorMap m_wh, m_wl;
-    int rc = make_tc_tmap(&m_wh, f->d_tc_wh, (int64_t)f->tc_blocks * BN, kp, BN / CL);
+    int rc = make_tc_tmap(&m_wh, f->d_tc_wh, (int64_t)f->tc_blocks * BN, kp, BN / CL, bk);
     if (rc) return rc;
-    rc = make_tc_tmap(&m_wl, f->d_tc_wl, (int64_t)f->tc_blocks * BN, kp, BN / CL);
+    rc = make_tc_tmap(&m_wl, f->d_tc_wl, (int64_t)f->tc_blocks * BN, kp, BN / CL, bk);
     if (rc) return rc;
     const int sms = device_sm_count(f->device);
     const size_t prep_smem = (size_t)32 * (kp + 1) * 4;
@@ -1155,17 +1180,23 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
     const bool hook = eb_scale != 1.0f;
     KernelFn kern = nullptr;
-    if (CL == 1) kern = hook ? score_ext_tc_kernel<true, 1> : score_ext_tc_kernel<false, 1>;
-    else if (CL == 2) kern = hook ? score_ext_tc_kernel<true, 2> : score_ext_tc_kernel<false, 2>;
-    else kern = hook ? score_ext_tc_kernel<true, 4> : score_ext_tc_kernel<false, 4>;
-    IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    if (bk == 32) {
+        if (CL == 1) kern = hook ? score_ext_tc_kernel<true, 1, 32> : score_ext_tc_kernel<false, 1, 32>;
+        else if (CL == 2) kern = hook ? score_ext_tc_kernel<true, 2, 32> : score_ext_tc_kernel<false, 2, 32>;
+        else kern = hook ? score_ext_tc_kernel<true, 4, 32> : score_ext_tc_kernel<false, 4, 32>;
+    } else {
+        if (CL == 1) kern = hook ? score_ext_tc_kernel<true, 1, 16> : score_ext_tc_kernel<false, 1, 16>;
+        else if (CL == 2) kern = hook ? score_ext_tc_kernel<true, 2, 16> : score_ext_tc_kernel<false, 2, 16>;
+        else kern = hook ? score_ext_tc_kernel<true, 4, 16> : score_ext_tc_kernel<false, 4, 16>;
+    }
+    IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     // how many clusters are co-resident (one CTA per SM; clusters never span GPCs)
     int max_clusters = sms / CL;
     if (CL > 1) {
         cudaLaunchConfig_t qc = {};
         qc.gridDim = dim3((unsigned)(sms / CL * CL));
         qc.blockDim = dim3(THREADS);
-        qc.dynamicSmemBytes = SMEM_BYTES;
+        qc.dynamicSmemBytes = smem_bytes;
         cudaLaunchAttribute qa[1];
         qa[0].id = cudaLaunchAttributeClusterDimension;
         qa[0].val.clusterDim.x = (unsigned)CL;
@@ -1186,9 +1217,9 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
         IFB_CUDA(cudaGetLastError());
         count_launch();
         CUtensorMap m_xh, m_xl;
-        rc = make_tc_tmap(&m_xh, xh, rows, kp, BM);
+        rc = make_tc_tmap(&m_xh, xh, rows, kp, BM, bk);
         if (rc) return rc;
-        rc = make_tc_tmap(&m_xl, xl, rows, kp, BM);
+        rc = make_tc_tmap(&m_xl, xl, rows, kp, BM, bk);
         if (rc) return rc;
         Params p;
         p.meta = f->d_tc_meta;
@@ -1221,7 +1252,7 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(THREADS);
-        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
