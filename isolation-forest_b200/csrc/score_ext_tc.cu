@@ -83,8 +83,9 @@ constexpr uint32_t META_BYTES = sizeof(BlockMeta);
 // Operand stage geometry and shared-memory carve-up (offsets from a 1024-aligned base) for a K chunk of BKT elements per
 // stage.  BKT = 32: 64-byte rows (64B swizzle), two k-steps per stage, 3 stages of 48 KB.  BKT = 16: 32-byte rows (32B
 // swizzle), one k-step per stage, 6 stages of 24 KB -- the same bytes, but five stages instead of two in flight while one
-// is consumed: wide hyperplanes are bound by the latency of the operand feed (the MMA issuer waited for operands 31 % of
-// the time with 3 x 48 KB, profiles/r02_score_ext_tc_v10_ncu.md).
+// is consumed.  Built to test whether wide hyperplanes are bound by the LATENCY of the operand feed (the MMA issuer waits
+// for operands 31 % of the time with 3 x 48 KB): they are not -- 400K x 1024 rows, 256 trees: 47.0 ms against 41.9 ms,
+// operand waits 35 % -- so BKT = 32 stays the default and IFB_TC_BK=16 the experiment.
 template <int BKT>
 struct Geo {
     static_assert(BKT == 16 || BKT == 32, "K chunk of one or two 16-wide k-steps");
@@ -1164,8 +1165,9 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     // pack the 148 SMs exactly.
     const int cl_env = getenv("IFB_TC_CLUSTER") ? atoi(getenv("IFB_TC_CLUSTER")) : (kp >= 256 ? 4 : 2);
     const int CL = (cl_env == 1 || cl_env == 4) ? cl_env : 2;
-    // K chunk per operand stage (IFB_TC_BK = 16 | 32 overrides): wide hyperplanes take 6 fine stages, see Geo
-    const int bk_env = getenv("IFB_TC_BK") ? atoi(getenv("IFB_TC_BK")) : (kp >= 256 ? 16 : 32);
+    // K chunk per operand stage (IFB_TC_BK = 16 selects the 6 x 24 KB ring, measured SLOWER: the feed is bound by the
+    // bytes written into shared memory per MMA cycle, not by the latency of a stage, and 32-byte rows cost TMA efficiency)
+    const int bk_env = getenv("IFB_TC_BK") ? atoi(getenv("IFB_TC_BK")) : 32;
     const int bk = bk_env == 16 ? 16 : 32;
     const uint32_t smem_bytes = bk == 16 ? Geo<16>::SMEM_BYTES : Geo<32>::SMEM_BYTES;
     CUtensorMap m_wh, m_wl;
