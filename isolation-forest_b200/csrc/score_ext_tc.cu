@@ -86,13 +86,18 @@ constexpr uint32_t META_BYTES = sizeof(BlockMeta);
 // is consumed.  Built to test whether wide hyperplanes are bound by the LATENCY of the operand feed (the MMA issuer waits
 // for operands 31 % of the time with 3 x 48 KB): they are not -- 400K x 1024 rows, 256 trees: 47.0 ms against 41.9 ms,
 // operand waits 35 % -- so BKT = 32 stays the default and IFB_TC_BK=16 the experiment.
-template <int BKT>
+// CG = 2: the two CTAs of a cluster form one tcgen05 `cta_group::2` pair -- ONE MMA instruction (issued by the even CTA)
+// multiplies the 2 x 128 rows of both CTAs with the block's 256 hyperplanes, each CTA holding only HALF of the
+// hyperplane tile in its shared memory (the tensor cores of the pair read both halves): 32 KB instead of 48 KB written
+// into a CTA's shared memory per stage, four stages instead of three.
+template <int BKT, int CG = 1>
 struct Geo {
     static_assert(BKT == 16 || BKT == 32, "K chunk of one or two 16-wide k-steps");
+    static_assert(CG == 1 || (CG == 2 && BKT == 32), "the CTA-pair variant uses 64-byte rows");
     static constexpr int BK = BKT;
-    static constexpr int STAGES = BKT == 32 ? 3 : 6;
+    static constexpr int STAGES = CG == 2 ? 4 : (BKT == 32 ? 3 : 6);
     static constexpr uint32_t A_BYTES = BM * BKT * 2;
-    static constexpr uint32_t B_BYTES = BN * BKT * 2;
+    static constexpr uint32_t B_BYTES = (BN / CG) * BKT * 2;
     static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // xh, xl, wh, wl
     static constexpr uint32_t OFF_STAGES = 0;
     static constexpr uint32_t OFF_MASKS = OFF_STAGES + STAGES * STAGE_BYTES;   // [2 teams][4 quarters]: {left, ambiguous} words [8][32]
@@ -172,6 +177,29 @@ __device__ __forceinline__ bool mbar_poll(uint32_t bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
+// the same with cluster scope: for a barrier that threads of the PEER CTA arrive on (release.cluster)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((spin & 0xFFFFu) == 0xFFFFu) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t0 == 0) t0 = t1;
+            else if (t1 - t0 > 4000000000ull) __trap();
+        }
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_poll(bar, parity)) return;
     unsigned long long t0;
@@ -208,6 +236,21 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *
         "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
         : "memory");
 }
+// cta_group::2 flavours (CUTLASS sm100: SM100_TMA_2SM_LOAD, SM100_MMA_F16BF16_2x1SM_SS, umma_arrive_multicast_2x1SM).
+// The load signals the mbarrier at `bar`, which may live in the PEER CTA of the pair (shared::cluster address).
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap *map, int32_t c0, int32_t c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], "
+        "[%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// shared::cluster address of the same shared-memory offset in the EVEN CTA of the pair (bit 24 of a shared window
+// address is the CTA's rank parity inside its pair: cute::Sm100MmaPeerBitMask)
+__device__ __forceinline__ uint32_t pair_leader_addr(uint32_t a) { return a & 0xFEFFFFFFu; }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -234,6 +277,22 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// the pair's MMA: D of BOTH CTAs (+)= A (each CTA's own rows) * B (half in each CTA's shared memory)
+__device__ __forceinline__ void umma_f16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
 }
 // mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -317,11 +376,13 @@ __device__ __forceinline__ bool exact_left(const float *__restrict__ xr, const f
 // B tile from L2 ONCE: CTA r loads rows [r*256/CL, (r+1)*256/CL) of wh / wl and TMA-multicasts them into the same stage
 // of all CL CTAs (the operand feed, not the MMA, bounds this kernel: 48 KB per stage per SM from L2 without sharing).
 // A stage may be refilled once the MMAs of ALL CL CTAs have read it: tcgen05.commit arrives on every CTA's empty barrier.
-template <bool HOOK, int CL, int BKT>
+template <bool HOOK, int CL, int BKT, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                     const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, const Params p) {
-    using G = Geo<BKT>;
+    using G = Geo<BKT, CG>;
+    constexpr bool PAIR = CG == 2;   // the cluster's two CTAs are one cta_group::2 pair (see Geo)
+    static_assert(!PAIR || CL == 2, "a pair is a cluster of two");
     constexpr int BK = G::BK, STAGES = G::STAGES;
     constexpr uint32_t A_BYTES = G::A_BYTES, B_BYTES = G::B_BYTES, STAGE_BYTES = G::STAGE_BYTES, OFF_STAGES = G::OFF_STAGES,
                        OFF_MASKS = G::OFF_MASKS, OFF_LV = G::OFF_LV, OFF_LD = G::OFF_LD, OFF_META = G::OFF_META,
@@ -346,11 +407,12 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), CL);   // one commit per CTA of the cluster
+            mbar_init(bar_empty(s), PAIR ? 1 : CL);   // one commit per CTA of the cluster (one for the whole pair)
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(bar_tfull(b), 1);
-            mbar_init(bar_tempty(b), EPI_WARPS / 2);    // the eight warps of the pair that owns this accumulator buffer
+            // the eight warps of the team that owns this accumulator buffer -- of BOTH CTAs when the pair shares the MMA
+            mbar_init(bar_tempty(b), PAIR ? EPI_WARPS : EPI_WARPS / 2);
             // every LANE arrives on the leaf-buffer barriers, releasing its own shared-memory accesses (no reliance on a
             // warp-level sync in front of a single arrive: also what compute-sanitizer's racecheck can follow)
             mbar_init(bar_lvfull(b), EPI_WARPS / 2 * 32);
@@ -363,9 +425,15 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulator buffers); this warp also frees them
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_ptr_s)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {   // the same warp of both CTAs, the same destination offset (cute::TMEM::Allocator2Sm)
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_ptr_s)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_ptr_s)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -393,6 +461,22 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                     for (int kc = 0; kc < KC; kc++) {
                         mbar_wait_timed(bar_empty(stage), phase ^ 1u, &w_empty, st_on);
                         const uint32_t st = base + OFF_STAGES + (uint32_t)stage * STAGE_BYTES;
+                        if constexpr (PAIR) {
+                            // both CTAs' loads report to the EVEN CTA's barrier, which expects the bytes of both; each CTA
+                            // brings its own rows and its own half of the block's hyperplanes
+                            constexpr int HN = BN / 2;
+                            const uint32_t fb = pair_leader_addr(bar_full(stage));
+                            if (cta_rank == 0) mbar_expect_tx(bar_full(stage), 2 * STAGE_BYTES);
+                            tma_load_2d_cg2(st, &map_xh, kc * BK, (int32_t)(tile * BM), fb);
+                            tma_load_2d_cg2(st + A_BYTES, &map_xl, kc * BK, (int32_t)(tile * BM), fb);
+                            tma_load_2d_cg2(st + 2 * A_BYTES, &map_wh, kc * BK, b * BN + (int)cta_rank * HN, fb);
+                            tma_load_2d_cg2(st + 2 * A_BYTES + B_BYTES, &map_wl, kc * BK, b * BN + (int)cta_rank * HN, fb);
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                            continue;
+                        }
                         mbar_expect_tx(bar_full(stage), STAGE_BYTES);
                         tma_load_2d(st, &map_xh, kc * BK, (int32_t)(tile * BM), bar_full(stage));
                         tma_load_2d(st + A_BYTES, &map_xl, kc * BK, (int32_t)(tile * BM), bar_full(stage));
@@ -423,8 +507,8 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread issues for the whole CTA =====
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(BM, BN);
+        if (lane == 0 && (!PAIR || cta_rank == 0)) {   // the pair's MMAs are issued by its even CTA alone
+            const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
@@ -434,7 +518,9 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int b = 0; b < NB; b++, it++) {
                     const int buf = (int)(it & 1u);
-                    mbar_wait_timed(bar_tempty(buf), ((it >> 1) & 1u) ^ 1u, &w_tempty, st_on);   // the epilogue has drained this accumulator buffer
+                    // the epilogue (of both CTAs of a pair) has drained this accumulator buffer
+                    if constexpr (PAIR) mbar_wait_cluster(bar_tempty(buf), ((it >> 1) & 1u) ^ 1u);
+                    else mbar_wait_timed(bar_tempty(buf), ((it >> 1) & 1u) ^ 1u, &w_tempty, st_on);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
                     for (int kc = 0; kc < KC; kc++) {
@@ -448,19 +534,28 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                             const uint64_t a_l = desc(st + A_BYTES + ks * 32);
                             const uint64_t b_h = desc(st + 2 * A_BYTES + ks * 32);
                             const uint64_t b_l = desc(st + 2 * A_BYTES + B_BYTES + ks * 32);
-                            umma_f16(d_tmem, a_h, b_h, idesc, (kc | ks) != 0 ? 1u : 0u);
-                            umma_f16(d_tmem, a_l, b_h, idesc, 1u);
-                            umma_f16(d_tmem, a_h, b_l, idesc, 1u);
+                            if constexpr (PAIR) {
+                                umma_f16_cg2(d_tmem, a_h, b_h, idesc, (kc | ks) != 0 ? 1u : 0u);
+                                umma_f16_cg2(d_tmem, a_l, b_h, idesc, 1u);
+                                umma_f16_cg2(d_tmem, a_h, b_l, idesc, 1u);
+                            } else {
+                                umma_f16(d_tmem, a_h, b_h, idesc, (kc | ks) != 0 ? 1u : 0u);
+                                umma_f16(d_tmem, a_l, b_h, idesc, 1u);
+                                umma_f16(d_tmem, a_h, b_l, idesc, 1u);
+                            }
                         }
                         // the stage may be refilled once these MMAs -- and the peers' -- have read it
-                        if constexpr (CL == 1) umma_commit(bar_empty(stage));
+                        if constexpr (PAIR) umma_commit_cg2_mc(bar_empty(stage), kClusterMask);
+                        else if constexpr (CL == 1) umma_commit(bar_empty(stage));
                         else umma_commit_mc(bar_empty(stage), kClusterMask);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1u;
                         }
                     }
-                    umma_commit(bar_tfull(buf));   // accumulators of this block are complete
+                    // accumulators of this block are complete (in both CTAs of a pair)
+                    if constexpr (PAIR) umma_commit_cg2_mc(bar_tfull(buf), kClusterMask);
+                    else umma_commit(bar_tfull(buf));
                 }
             }
             if (st_on) {
@@ -623,7 +718,10 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
                 // the accumulator buffer is free as soon as every warp's chunks are in its registers / masks
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty(buf));
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_cluster(pair_leader_addr(bar_tempty(buf)));   // the issuing CTA's barrier
+                    else mbar_arrive(bar_tempty(buf));
+                }
                 if (st_on) c_drain += (unsigned long long)(clock64() - t_drain0);
                 asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * PW) : "memory");   // the team's 8 mask words are complete
                 // the summing warp has consumed the leaf values this buffer held two blocks ago
@@ -755,7 +853,8 @@ score_ext_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     if constexpr (CL > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it / signal it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -1164,12 +1263,17 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     // 200 trees: 66.5 / 66.6 / 74.4 ms -- clusters of four strand a few SMs per GPC) and take clusters of two, which
     // pack the 148 SMs exactly.
     const int cl_env = getenv("IFB_TC_CLUSTER") ? atoi(getenv("IFB_TC_CLUSTER")) : (kp >= 256 ? 4 : 2);
-    const int CL = (cl_env == 1 || cl_env == 4) ? cl_env : 2;
+    int CL = (cl_env == 1 || cl_env == 4) ? cl_env : 2;
     // K chunk per operand stage (IFB_TC_BK = 16 selects the 6 x 24 KB ring, measured SLOWER: the feed is bound by the
     // bytes written into shared memory per MMA cycle, not by the latency of a stage, and 32-byte rows cost TMA efficiency)
     const int bk_env = getenv("IFB_TC_BK") ? atoi(getenv("IFB_TC_BK")) : 32;
     const int bk = bk_env == 16 ? 16 : 32;
-    const uint32_t smem_bytes = bk == 16 ? Geo<16>::SMEM_BYTES : Geo<32>::SMEM_BYTES;
+    // cta_group::2 pairs (IFB_TC_CG = 1 | 2 overrides): wide hyperplanes are bound by the bytes written into a CTA's
+    // shared memory per MMA cycle; a pair halves the hyperplane tile per CTA
+    const int cg_env = getenv("IFB_TC_CG") ? atoi(getenv("IFB_TC_CG")) : 1;
+    const int cg = (cg_env == 2 && bk == 32) ? 2 : 1;
+    const uint32_t smem_bytes = cg == 2 ? Geo<32, 2>::SMEM_BYTES : (bk == 16 ? Geo<16>::SMEM_BYTES : Geo<32>::SMEM_BYTES);
+    if (cg == 2) CL = 2;
     CUtensorMap m_wh, m_wl;
     int rc = make_tc_tmap(&m_wh, f->d_tc_wh, (int64_t)f->tc_blocks * BN, kp, BN / CL, bk);
     if (rc) return rc;
@@ -1182,14 +1286,16 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
     const bool hook = eb_scale != 1.0f;
     KernelFn kern = nullptr;
-    if (bk == 32) {
-        if (CL == 1) kern = hook ? score_ext_tc_kernel<true, 1, 32> : score_ext_tc_kernel<false, 1, 32>;
-        else if (CL == 2) kern = hook ? score_ext_tc_kernel<true, 2, 32> : score_ext_tc_kernel<false, 2, 32>;
-        else kern = hook ? score_ext_tc_kernel<true, 4, 32> : score_ext_tc_kernel<false, 4, 32>;
+    if (cg == 2) {
+        kern = hook ? score_ext_tc_kernel<true, 2, 32, 2> : score_ext_tc_kernel<false, 2, 32, 2>;
+    } else if (bk == 32) {
+        if (CL == 1) kern = hook ? score_ext_tc_kernel<true, 1, 32, 1> : score_ext_tc_kernel<false, 1, 32, 1>;
+        else if (CL == 2) kern = hook ? score_ext_tc_kernel<true, 2, 32, 1> : score_ext_tc_kernel<false, 2, 32, 1>;
+        else kern = hook ? score_ext_tc_kernel<true, 4, 32, 1> : score_ext_tc_kernel<false, 4, 32, 1>;
     } else {
-        if (CL == 1) kern = hook ? score_ext_tc_kernel<true, 1, 16> : score_ext_tc_kernel<false, 1, 16>;
-        else if (CL == 2) kern = hook ? score_ext_tc_kernel<true, 2, 16> : score_ext_tc_kernel<false, 2, 16>;
-        else kern = hook ? score_ext_tc_kernel<true, 4, 16> : score_ext_tc_kernel<false, 4, 16>;
+        if (CL == 1) kern = hook ? score_ext_tc_kernel<true, 1, 16, 1> : score_ext_tc_kernel<false, 1, 16, 1>;
+        else if (CL == 2) kern = hook ? score_ext_tc_kernel<true, 2, 16, 1> : score_ext_tc_kernel<false, 2, 16, 1>;
+        else kern = hook ? score_ext_tc_kernel<true, 4, 16, 1> : score_ext_tc_kernel<false, 4, 16, 1>;
     }
     IFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     // how many clusters are co-resident (one CTA per SM; clusters never span GPCs)

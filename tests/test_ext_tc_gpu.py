@@ -143,6 +143,26 @@ def test_sparse_hyperplanes_take_the_tensor_core_path(nat, oracle, dev, n, d, T,
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("env", [{"IFB_TC_CG": "2"}, {"IFB_TC_BK": "16"}, {"IFB_TC_BK": "16", "IFB_TC_CLUSTER": "4"},
+                                 {"IFB_TC_CLUSTER": "1"}])
+@pytest.mark.parametrize("n,d,T", [(20_000, 64, 30), (3_000, 1024, 8)])
+def test_kernel_variants_agree_with_the_oracle(nat, oracle, dev, monkeypatch, env, n, d, T):
+    """The measured alternatives stay correct: the cta_group::2 pair (one tcgen05.mma for the 2 x 128 rows of a
+    two-CTA cluster, half of the hyperplane tile per CTA), the 32-byte-row operand ring, other cluster sizes."""
+    X = synth_mixture(n, d, 8100 + d)
+    t = oracle.fit_forest(X[:min(n, 20_000)], T, 256, random_seed=9, ext_level=d - 1)
+    F = nat.NativeForest.from_tables(t)
+    assert F.ext_tc_info()[1] > 0
+    Xs = X.copy()
+    Xs[3::101, 2] = np.nan
+    Xs[9::53, :] = 0.0
+    with np.errstate(all="ignore"):
+        ref = oracle.Forest(t).score(Xs, threads=8, want_parts=True)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    assert_parity(F.score_device(colmajor_cuda(Xs), want_parts=True), ref)
+
+
 def test_tc_special_values(nat, oracle, dev):
     n, d = 8192, 64
     X = synth_mixture(n, d, 77)
