@@ -1,8 +1,9 @@
-// Tensor-core scoring of fully-extended isolation forests (every hyperplane dense over all d features) for sm_100a.
+// Tensor-core scoring of extended isolation forests for sm_100a.
 //
 // Replaces ExtendedIsolationTree.pathLength (IF/extended/ExtendedIsolationTree.scala:283-355) and
-// SplitHyperplane.dot (IF/extended/ExtendedUtils.scala:36-55) for the BASELINE shapes with extensionLevel = d-1
-// (config 3: d = 64, config 5: d = 1024).  The per-row dot products of a walk are a contraction
+// SplitHyperplane.dot (IF/extended/ExtendedUtils.scala:36-55): BASELINE configs 3 (d = 64) and 5 (d = 1024) with
+// extensionLevel = d-1, and sparse hyperplanes (extensionLevel < d-1 or a feature subspace) as zero-padded columns.
+// The per-row dot products of a walk are a contraction
 //     S[row][node] = sum_i x[row][i] * w[node][i]
 // so ALL hyperplanes of the forest are evaluated as one [rows x nodes x d] GEMM on the 5th-generation tensor cores
 // (tcgen05.mma, accumulators in TMEM), and the walk itself only compares accumulators with offsets.
@@ -14,22 +15,28 @@
 //     |S' - offset'| > c_k * ||w'||_2 * 1  >=  c_k * ||w'||_2 * ||x'||_2      (c_k: bound constant)
 // which proves that the reference's comparison has the same outcome.  Every other visit ("stuck" lane, ~1e-5 of the
 // visits at d = 64, ~1e-3 at d = 1024, and every visit of a row with non-finite / out-of-range features) is decided by
-// the warp cooperatively with the reference's exact arithmetic (f32 product, f64 sum; lane-parallel re-association with
-// its own proven bound, else the sequential order).  Decisions are therefore bit-identical to the reference's.
+// the warp cooperatively with the reference's exact arithmetic on the STORED terms (f32 product, f64 sum; lane-parallel
+// re-association with its own proven bound, else the sequential order).  Decisions are bit-identical to the reference's.
 //
 // Kernels
+//   ext_tc_densify        sparse hyperplanes only: stored terms -> zero-filled rows of the matrix width (once per forest).
 //   ext_tc_prepare_cols   one warp per hyperplane: scale, fp16 hi/lo split, ||w'||, offset' and bound coefficient
 //                         (once per forest).
 //   ext_tc_prepare_rows   per call: row scaling, fp16 hi/lo split, row norm, row-major f32 copy for the exact path.
-//   score_ext_tc_kernel   persistent, warp-specialised: warp 0 = TMA producer (A = rows, B = hyperplanes, 64-byte
-//                         swizzled K-major tiles), warp 1 = tcgen05.mma issuer (128 x 256 x 16 fp16, f32 accumulators,
-//                         two 256-column TMEM buffers), warps 2-17 = epilogue.  Four epilogue warps share a TMEM lane
-//                         quarter (32 rows).  Drain, split by COLUMNS: each warp tcgen05.ld's two 32-column chunks of
-//                         the block and turns every accumulator into two bits (left? / ambiguous?) appended to
-//                         per-lane mask words (no per-column store); the quad's 16 mask words meet in shared memory.
-//                         Walk, split by TREES: each warp walks a quarter of the block's trees on the masks (up to
-//                         4 chains in flight per lane), resolves ambiguous visits exactly and hands the leaf values
-//                         to the quad's first warp, which adds them in tree order (the reference's sequential f32 sum).
+//   score_ext_tc_kernel   persistent, warp-specialised, 640 threads, one CTA per SM in clusters of 2 or 4:
+//     warp 0   one lane: TMA producer of the operand stages (A = rows, B = hyperplanes, 64-byte swizzled K-major tiles;
+//              the B tiles are fetched once per cluster with TMA multicast);
+//     warp 1   one lane: tcgen05.mma issuer (128 x 256 x 16 fp16, f32 accumulators, two 256-column TMEM buffers);
+//     warps 2-17  epilogue, four per TMEM lane quarter (= per scheduler), working as two TEAMS on alternate blocks.
+//              Drain, split by COLUMNS: each warp tcgen05.ld's its 32-column chunks and turns every accumulator into a
+//              "left?" bit appended to per-lane mask words, with ONE chunk-wide ambiguity test (smallest |dlt| against
+//              the largest bound); per-column "ambiguous?" bits only for chunks that fail it.  Walk, split by TREES, on
+//              the masks (up to 4 chains per lane, leaves point at themselves); ambiguous visits are resolved exactly;
+//              leaf values and depths go to shared memory;
+//     warp 18  adds every block's leaf values in tree order (the reference's sequential f32 sum) and writes the results;
+//     warp 19  one lane: feeds the ring of block descriptors (node tables), independent of the operand stages.
+//   Measured alternatives kept as opt-ins: IFB_TC_CG=2, the two CTAs of a cluster as one cta_group::2
+//   pair (one MMA for 2 x 128 rows, half of the hyperplane tile per CTA); IFB_TC_BK=16, six 24 KB stages of 32-byte rows.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
