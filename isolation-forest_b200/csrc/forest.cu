@@ -716,25 +716,17 @@ int ifb_host_free(void *ptr) {
     if (ptr) IFB_CUDA(cudaFreeHost(ptr));
     return IFB_OK;
 }
-// Served from the device's stream-ordered pool (the legacy default stream; the pool keeps freed blocks, see
-// tune_mempool): a cudaMalloc / cudaFree pair synchronises the whole device and cost a quarter of a small fit.  The
-// allocation is synchronised before it is handed out, the free waits for the legacy stream (which, by CUDA's rules, has
-// waited for every blocking stream); work queued on NON-blocking streams must be complete before a buffer is freed --
-// the contract cudaFree users already follow in practice.
+// Plain cudaMalloc / cudaFree on purpose: these buffers are what ifb_ipc_export hands to peer processes (the fused
+// tree-sharded scatter), and cudaIpcGetMemHandle refuses memory from the stream-ordered pool.
 int ifb_device_alloc(int32_t device, size_t bytes, void **ptr) {
     IFB_REQUIRE(ptr, "ptr is null");
     DeviceGuard dg(device);
-    tune_mempool(device);
-    IFB_CUDA(cudaMallocAsync(ptr, bytes ? bytes : 1, 0));
-    IFB_CUDA(cudaStreamSynchronize(0));
+    IFB_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
     return IFB_OK;
 }
 int ifb_device_free(int32_t device, void *ptr) {
     DeviceGuard dg(device);
-    if (ptr) {
-        IFB_CUDA(cudaStreamSynchronize(0));
-        IFB_CUDA(cudaFreeAsync(ptr, 0));
-    }
+    if (ptr) IFB_CUDA(cudaFree(ptr));
     return IFB_OK;
 }
 

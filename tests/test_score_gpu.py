@@ -487,3 +487,17 @@ def test_peer_flag_barrier_emulated(nat, dev):
         torch.cuda.synchronize()
         for r in range(world):
             assert flags[r][:world].tolist() == [epoch] * world
+
+
+def test_device_buffers_can_be_exported_to_peer_processes(nat, dev):
+    """The fused tree-sharded scatter hands ifb_device_alloc buffers to peer ranks through CUDA IPC: the allocation
+    must stay a plain device allocation (memory from the stream-ordered pool cannot be exported)."""
+    import ctypes as C
+    p = C.c_void_p()
+    nat.check(nat.lib().ifb_device_alloc(dev, 1 << 20, C.byref(p)))
+    try:
+        handle = C.create_string_buffer(64)
+        nat.check(nat.lib().ifb_ipc_export(dev, p, handle))
+        assert any(handle.raw)
+    finally:
+        nat.check(nat.lib().ifb_device_free(dev, p))
