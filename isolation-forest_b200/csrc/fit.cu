@@ -1333,9 +1333,9 @@ extern "C" int ifb_fit_device(int32_t device, const float *X, int64_t n_rows, in
     const size_t per_node = 4 + 4 + 8 + (ext ? 8 + 4 : 4 + 8);
     // hyperplane rows of all trees ride in the same batch when they are small enough to stage whole
     const size_t hp_elems = ext ? T * (size_t)cap_internal * k : 0;
-    // wide dense hyperplanes (k == d > 64: indices are 0..k-1 by construction) never leave the device: the forest
+    // dense hyperplanes (k == d: indices are 0..k-1 by construction) never leave the device: the forest
     // gathers its scoring tables from the builder's weight array directly (forest.cu::create_extended_from_device)
-    const bool hp_on_device = ext && k == d && k > 64 && std::getenv("IFB_FIT_HOST_HP") == nullptr;
+    const bool hp_on_device = ext && k == d && std::getenv("IFB_FIT_HOST_HP") == nullptr;
     const bool hp_staged = ext && !hp_on_device && hp_elems * 8 <= ((size_t)64 << 20);
     const size_t stage_bytes = T * 8 + T * (size_t)cap * per_node + (hp_staged ? hp_elems * 8 + 16 : 0) + 64;
     if ((rc = g_stage.reserve(stage_bytes))) return rc;

@@ -159,7 +159,7 @@ int build_standard_tables(ifb_forest *f) {
     return IFB_OK;
 }
 
-// ---- device-resident hyperplanes (forests fitted on the device, k == d > 64) ---------------------------------------
+// ---- device-resident hyperplanes (forests fitted on the device with k == d) ---------------------------------------
 namespace {
 // slot s of the scoring layout <- row slot_src[s] of the builder's weight array (one warp per slot); also the slot's
 // sum |w| and ||w||_2 (f64, the bounds of the exact / f32 tiers) and the "weights are f32-tier safe" flag
@@ -302,8 +302,6 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
     std::vector<double> wabs((size_t)internal, 0.0), wnorm((size_t)internal, 0.0);
     std::vector<WideNode> wn((size_t)total);
     std::vector<int32_t> tslot((size_t)std::max(T, 1), -1);
-    std::vector<unsigned char> blob;
-    std::vector<int64_t> boff(T + 1, 0);
     int rc;
     if ((rc = up((void **)&f->d_ext_w, dev ? nullptr : w.data(), (size_t)internal * k * 4))) return rc;
     if (!f->ext_dense_identity)
@@ -361,8 +359,62 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
         f->ext_w_safe = wsafe;
     }
     lap("bounds, wide-node records");
-    // ---- per-tree blobs for the dense kernel ----
-    if (f->ext_dense_identity && k <= 64) {
+    // (the per-tree blobs of the dense CUDA-core kernel are built on first use: ensure_ext_blob)
+    rc = commit();
+    lap("arena allocated, uploads queued");
+    if (rc) return rc;
+    if (dev && internal > 0) {
+        int64_t *d_src = nullptr;
+        int32_t *d_flag = nullptr;
+        IFB_CUDA(cudaMalloc((void **)&d_src, (size_t)internal * 8 + 16));
+        d_flag = reinterpret_cast<int32_t *>(d_src + internal);
+        IFB_CUDA(cudaMemcpyAsync(d_src, slot_src.data(), (size_t)internal * 8, cudaMemcpyHostToDevice, 0));
+        IFB_CUDA(cudaMemsetAsync(d_flag, 0, 4, 0));
+        ext_gather_weights_kernel<<<(unsigned)((internal + 7) / 8), 256>>>(dev->w, d_src, internal, k, f->d_ext_w, f->d_ext_wabs,
+                                                                            f->d_ext_wnorm, d_flag);
+        ext_patch_wide_nodes_kernel<<<(unsigned)((total + 255) / 256), 256>>>(reinterpret_cast<WideNode *>(f->d_ext_wide_nodes),
+                                                                                total, f->d_ext_wnorm);
+        count_launch(2);
+        int32_t unsafe = 0;
+        cudaError_t e = cudaMemcpy(&unsafe, d_flag, 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_src);
+        IFB_CUDA(e);
+        IFB_CUDA(cudaGetLastError());
+        f->ext_w_safe = unsafe == 0;
+    }
+    // tensor-core layout (fully-extended forests, and sparse hyperplanes as zero-padded columns; a forest that does not
+    // qualify simply keeps tc_ok = false)
+    if (internal > 0 && getenv("IFB_EXT_NO_TC") == nullptr && (f->ext_dense_identity || getenv("IFB_TC_NO_SPARSE") == nullptr)) {
+        rc = build_ext_tc_tables(f, child, hp, leaf, off, depthv, len);
+        if (rc) return rc;
+        lap("tensor-core tables");
+    }
+    return IFB_OK;
+}
+
+// Per-tree blobs of score_ext_dense_kernel (fully-extended forests with k <= 64; the fallback when the tensor-core path
+// does not take a call: IFB_EXT_NO_TC, a matrix wider than the forest, weights outside the fp16-safe range).  Built on
+// first use from the device-resident tables, so that creating / fitting a forest never pays for them.
+int ensure_ext_blob(ifb_forest *f) {
+    std::lock_guard<std::mutex> lk(f->plan_mu);
+    if (f->ext_blob_tried) return IFB_OK;
+    f->ext_blob_tried = true;
+    const int k = f->max_nnz;
+    if (!(f->ext_dense_identity && k <= 64) || f->ext_internal_slots == 0) return IFB_OK;
+    const int T = f->num_trees;
+    const int64_t total = f->node_off[T];
+    DeviceGuard dg(f->device);
+    std::vector<int32_t> child((size_t)total), hp((size_t)total);
+    std::vector<float> leaf((size_t)total), w((size_t)f->ext_internal_slots * k);
+    std::vector<double> off((size_t)total);
+    IFB_CUDA(cudaMemcpy(child.data(), f->d_ext_child, (size_t)total * 4, cudaMemcpyDeviceToHost));
+    IFB_CUDA(cudaMemcpy(hp.data(), f->d_ext_hp, (size_t)total * 4, cudaMemcpyDeviceToHost));
+    IFB_CUDA(cudaMemcpy(leaf.data(), f->d_ext_leaf, (size_t)total * 4, cudaMemcpyDeviceToHost));
+    IFB_CUDA(cudaMemcpy(off.data(), f->d_ext_off, (size_t)total * 8, cudaMemcpyDeviceToHost));
+    IFB_CUDA(cudaMemcpy(w.data(), f->d_ext_w, w.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> blob;
+    std::vector<int64_t> boff((size_t)T + 1, 0);
+    {
         const int D = k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64;
         const int WS = D + 4;  // row stride in floats: 16-byte units odd => per-lane LDS.128 gathers spread over banks
         int64_t mx = 0;
@@ -407,41 +459,20 @@ int build_extended_tables(ifb_forest *f, const DeviceHyperplanes *dev) {
             boff[t + 1] = (int64_t)blob.size();
             mx = std::max<int64_t>(mx, (int64_t)bpad);
         }
-        f->ext_blob_D = D;
+        unsigned char *dev_blob = nullptr;
+        const size_t b_blob = (blob.size() + 255) & ~(size_t)255;
+        IFB_CUDA(cudaMalloc((void **)&dev_blob, b_blob + boff.size() * 8));
+        cudaError_t e = cudaMemcpy(dev_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dev_blob + b_blob, boff.data(), boff.size() * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(dev_blob);
+            IFB_CUDA(e);
+        }
+        f->d_ext_blob = dev_blob;
+        f->d_ext_blob_off = reinterpret_cast<int64_t *>(dev_blob + b_blob);
+        f->device_bytes += (int64_t)(b_blob + boff.size() * 8);
         f->ext_blob_max = mx;
-
-        if ((rc = up((void **)&f->d_ext_blob, blob.data(), blob.size()))) return rc;
-        if ((rc = up((void **)&f->d_ext_blob_off, boff.data(), boff.size() * 8))) return rc;
-    }
-    lap("dense-kernel blobs");
-    rc = commit();
-    lap("arena allocated, uploads queued");
-    if (rc) return rc;
-    if (dev && internal > 0) {
-        int64_t *d_src = nullptr;
-        int32_t *d_flag = nullptr;
-        IFB_CUDA(cudaMalloc((void **)&d_src, (size_t)internal * 8 + 16));
-        d_flag = reinterpret_cast<int32_t *>(d_src + internal);
-        IFB_CUDA(cudaMemcpyAsync(d_src, slot_src.data(), (size_t)internal * 8, cudaMemcpyHostToDevice, 0));
-        IFB_CUDA(cudaMemsetAsync(d_flag, 0, 4, 0));
-        ext_gather_weights_kernel<<<(unsigned)((internal + 7) / 8), 256>>>(dev->w, d_src, internal, k, f->d_ext_w, f->d_ext_wabs,
-                                                                            f->d_ext_wnorm, d_flag);
-        ext_patch_wide_nodes_kernel<<<(unsigned)((total + 255) / 256), 256>>>(reinterpret_cast<WideNode *>(f->d_ext_wide_nodes),
-                                                                                total, f->d_ext_wnorm);
-        count_launch(2);
-        int32_t unsafe = 0;
-        cudaError_t e = cudaMemcpy(&unsafe, d_flag, 4, cudaMemcpyDeviceToHost);
-        cudaFree(d_src);
-        IFB_CUDA(e);
-        IFB_CUDA(cudaGetLastError());
-        f->ext_w_safe = unsafe == 0;
-    }
-    // tensor-core layout (fully-extended forests, and sparse hyperplanes as zero-padded columns; a forest that does not
-    // qualify simply keeps tc_ok = false)
-    if (internal > 0 && getenv("IFB_EXT_NO_TC") == nullptr && (f->ext_dense_identity || getenv("IFB_TC_NO_SPARSE") == nullptr)) {
-        rc = build_ext_tc_tables(f, child, hp, leaf, off, depthv, len);
-        if (rc) return rc;
-        lap("tensor-core tables");
+        f->ext_blob_D = D;   // last: launch_score_extended keys on it
     }
     return IFB_OK;
 }
@@ -628,7 +659,7 @@ int ensure_std_generic_tables(ifb_forest *f) {
 }  // namespace ifb
 
 namespace ifb {
-// Forest from the device builder's output without a host copy of the hyperplanes (fit.cu, k == d > 64): the node
+// Forest from the device builder's output without a host copy of the hyperplanes (fit.cu, k == d): the node
 // structure comes from the host tables, the weight rows are gathered on the device.  The builder guarantees the
 // SplitHyperplane invariants (ExtendedUtils.scala:27-34): k distinct ascending indices 0..k-1.
 int create_extended_from_device(int32_t device, int32_t num_trees, const int32_t *node_off, const int32_t *left,
@@ -677,7 +708,8 @@ ifb_forest::~ifb_forest() {
     cudaFree(d_gfeat);
     cudaFree(d_gchild);
     cudaFree(d_groot);
-    cudaFree(d_ext_arena);   // every d_ext_* table is a slice of it
+    cudaFree(d_ext_arena);   // every d_ext_* table is a slice of it ...
+    cudaFree(d_ext_blob);    // ... except the lazily built dense-kernel blobs (d_ext_blob_off is a slice of this one)
     cudaFree(d_tc_arena);    // every d_tc_* table is a slice of it ...
     cudaFree(d_tc_slot_len); // ... except the per-slot term counts of sparse forests
 }

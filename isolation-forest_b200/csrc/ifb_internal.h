@@ -161,7 +161,8 @@ struct ifb_forest {
     unsigned char *d_ext_blob = nullptr;
     int64_t *d_ext_blob_off = nullptr;   // [T+1] byte offsets (16-byte aligned)
     unsigned char *d_ext_arena = nullptr; // the one allocation every d_ext_* table above is a slice of
-    int32_t ext_blob_D = 0;              // padded hyperplane width (8/16/32/64), 0 = no blob layout
+    bool ext_blob_tried = false;         // ensure_ext_blob ran (the blobs are built on first use of the dense kernel)
+    int32_t ext_blob_D = 0;              // padded hyperplane width (8/16/32/64), 0 = no blob layout (yet)
     int64_t ext_blob_max = 0;            // largest blob in bytes
     bool ext_w_safe = false;             // every hyperplane weight is normal with 2^-60 <= |w| <= 2^40
 
@@ -200,6 +201,7 @@ int create_extended_from_device(int32_t device, int32_t num_trees, const int32_t
                                 const int32_t *right, const int64_t *num_instances, const double *offset, int32_t k,
                                 const DeviceHyperplanes &dev, int32_t num_samples, int32_t total_num_features,
                                 ifb_forest **out);
+int ensure_ext_blob(ifb_forest *f);   // dense CUDA-core kernel's per-tree blobs, built on first use
 int get_std_plan(ifb_forest *f, int32_t d, ifb_forest::StdPlan **out);   // *out = nullptr: no smem plan, use generic
 int ensure_std_generic_tables(ifb_forest *f);
 int launch_score_standard_generic(const ifb_forest *f, const float *X, int64_t n_rows, int32_t d, int64_t ld,

@@ -617,6 +617,10 @@ int launch_score_extended(const ifb_forest *f, const float *X, int64_t n_rows, i
         const int rc = launch_score_extended_tc(f, X, n_rows, d, ld, layout, scores, depth_sum, path_sum, accumulate_only, stream);
         if (rc >= 0) return rc;
     }
+    if (f->ext_dense_identity && f->max_nnz <= 64 && d <= 64 && getenv("IFB_EXT_GENERIC") == nullptr) {
+        const int brc = ensure_ext_blob(const_cast<ifb_forest *>(f));   // first call of this fallback builds its tables
+        if (brc) return brc;
+    }
     if (f->ext_blob_D > 0 && d <= 64 && getenv("IFB_EXT_GENERIC") == nullptr) {
         ScoreExtDenseParams q;
         q.X = X; q.n_rows = n_rows; q.ld = ld; q.d = d; q.layout = layout;

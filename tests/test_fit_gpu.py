@@ -159,10 +159,12 @@ def test_fit_host_reads_only_the_addressed_extent(nat, oracle):
     assert_tables_equal(nat.fit_host(wide[:, :d], prm).export(), ref)   # row-major, ld = d + 3
 
 
-def test_wide_extended_fit_keeps_the_hyperplanes_on_the_device(nat, oracle, monkeypatch):
-    """k == d > 64: the weights are gathered into the scoring tables on the device and only come back to the host on
-    export.  Tables (incl. every weight bit) == oracle == the host-staged build; scoring parity on the same forest."""
-    n_rows, d, T = 6000, 160, 7
+@pytest.mark.parametrize("d", [160, 64, 12])
+def test_fully_extended_fit_keeps_the_hyperplanes_on_the_device(nat, oracle, monkeypatch, d):
+    """k == d: the weights are gathered into the scoring tables on the device and only come back to the host on
+    export.  Tables (incl. every weight bit) == oracle == the host-staged build; scoring parity on the same forest, also
+    through the CUDA-core kernels (whose per-tree blobs, for d <= 64, are built on first use from the device tables)."""
+    n_rows, T = 6000, 7
     X = synth_mixture(n_rows, d, 300 + d)
     ref = oracle.fit_forest(X, T, 256, random_seed=2, ext_level=d - 1)
     F = fit_gpu(nat, X, T, 256, seed=2, ext=d - 1)
