@@ -1269,8 +1269,11 @@ int launch_score_extended_tc(const ifb_forest *f, const float *X, int64_t n_rows
     // per cluster) and take clusters of four; narrow ones are bound by the epilogue's instruction count (10M x 64,
     // 200 trees: 66.5 / 66.6 / 74.4 ms -- clusters of four strand a few SMs per GPC) and take clusters of two, which
     // pack the 148 SMs exactly.
-    const int cl_env = getenv("IFB_TC_CLUSTER") ? atoi(getenv("IFB_TC_CLUSTER")) : (kp >= 256 ? 4 : 2);
-    int CL = (cl_env == 1 || cl_env == 4) ? cl_env : 2;
+    // Final kernel (teams, summing warp, descriptor loader), 4M x 64 rows / 200 trees: 20.7 / 21.3 / 24.0 ms with 1 / 2 / 4
+    // CTAs per cluster -- an epilogue-bound kernel gains nothing from sharing operand loads and loses a little to the
+    // cluster's lockstep; 400K x 1024: 42.5 / 42.1 ms with 2 / 4.
+    const int cl_env = getenv("IFB_TC_CLUSTER") ? atoi(getenv("IFB_TC_CLUSTER")) : (kp >= 256 ? 4 : 1);
+    int CL = (cl_env == 2 || cl_env == 4) ? cl_env : 1;
     // K chunk per operand stage (IFB_TC_BK = 16 selects the 6 x 24 KB ring, measured SLOWER: the feed is bound by the
     // bytes written into shared memory per MMA cycle, not by the latency of a stage, and 32-byte rows cost TMA efficiency)
     const int bk_env = getenv("IFB_TC_BK") ? atoi(getenv("IFB_TC_BK")) : 32;
