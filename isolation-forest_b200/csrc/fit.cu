@@ -717,21 +717,26 @@ __global__ void __launch_bounds__(BT, EXT ? 2 : 4) fit_kernel(const FitDev p) {
                         }
                     }
                     // next task, as long as it is small too (otherwise the block takes over again)
+                    // (broadcast by shuffles, not through sh.cur: the other warps may still be reading the task the block
+                    // popped)
                     int go = 0;
+                    NodeTask nx = nd;
                     if (lane == 0) {
                         go = (sp > 0 && sh.stack[sp - 1].count <= 32 && nnodes < p.cap) ? 1 : 0;
                         if (go) {
-                            sh.cur = sh.stack[--sp];
+                            nx = sh.stack[--sp];
                             nid = nnodes++;
-                            if (sh.cur.is_right) o_right[sh.cur.parent] = nid;
+                            if (nx.is_right) o_right[nx.parent] = nid;
                         }
                     }
                     go = __shfl_sync(0xffffffffu, go, 0);
                     if (!go) break;
                     nid = __shfl_sync(0xffffffffu, nid, 0);
-                    __syncwarp();
-                    nd = sh.cur;
-                    __syncwarp();
+                    nd.start = __shfl_sync(0xffffffffu, nx.start, 0);
+                    nd.count = __shfl_sync(0xffffffffu, nx.count, 0);
+                    nd.height = __shfl_sync(0xffffffffu, nx.height, 0);
+                    nd.parent = __shfl_sync(0xffffffffu, nx.parent, 0);
+                    nd.is_right = __shfl_sync(0xffffffffu, nx.is_right, 0);
                 }
             }
             __syncthreads();
