@@ -44,6 +44,20 @@ for (n, d, T, ext) in ((3000, 32, 20, -1), (1500, 128, 30, -1), (700, 900, 6, -1
     thr, frac = nat.quantile_device(s, 0.9)                         # radix select
     lab = nat.predict_device(s, thr)
     print("ok", n, d, T, ext, flush=True)
+# measured alternatives of the tensor-core kernel (cta_group::2 pair, 32-byte-row ring) and the CUDA-core fallback whose
+# per-tree blobs are built on first use from a device-fitted forest
+X = rng.standard_normal((1500, 64)).astype(np.float32)
+F = nat.fit_device(cm(X), nat.FitParams(5, 256, 64, 0, 1, 1, 63, 0, 0))
+ref = O.Forest(F.export()).score(X, want_parts=True)
+for env in ({"IFB_TC_CG": "2"}, {"IFB_TC_BK": "16"}, {"IFB_EXT_NO_TC": "1"}):
+    os.environ.update(env)
+    s, ds, ps = F.score_device(cm(X), want_parts=True)
+    torch.cuda.synchronize()
+    for k in env:
+        del os.environ[k]
+    assert np.array_equal(ds.cpu().numpy(), ref[1]) and np.array_equal(ps.cpu().numpy(), ref[2]), env
+    print("variant ok", env, flush=True)
+
 # the opt-in rank-word standard kernel (score_std_rank.cu): bulk-copy tiles, a ragged tail, plain-load tiles
 os.environ["IFB_STD_RANK"] = "1"
 for (n, d, T) in ((2600, 32, 20), (1537, 7, 9)):
