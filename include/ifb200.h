@@ -65,6 +65,8 @@ IFB_API int ifb_device_count(int32_t *count);
 /* Pinned host memory for staging buffers (JNI: wrap with NewDirectByteBuffer). */
 IFB_API int ifb_host_alloc(size_t bytes, void **ptr);
 IFB_API int ifb_host_free(void *ptr);
+/* Device memory (plain cudaMalloc allocations on purpose: ifb_ipc_export can hand them to peer processes, which memory
+ * from a stream-ordered pool does not allow). */
 IFB_API int ifb_device_alloc(int32_t device, size_t bytes, void **ptr);
 IFB_API int ifb_device_free(int32_t device, void *ptr);
 /* Blocking copies between host memory and device memory obtained from ifb_device_alloc. */
